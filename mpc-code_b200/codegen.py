@@ -1,0 +1,213 @@
+"""Emit straight-line C / CUDA from expression DAGs.
+
+The reference gets its derivative code from CasADi's virtual machine at run time
+(``nlpsol`` builds gradient/Jacobian/Hessian functions, ``Control_Calc.py:258``).  Here the
+same information is produced once, ahead of time, as source text: one ``static`` function per
+map, taking ``const double*`` inputs and ``double*`` outputs, with common sub-expressions shared.
+The text compiles unchanged as a CUDA ``__device__`` function (macro ``MPCB_FN``) and as plain C.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Sequence, Tuple
+
+from . import symbolic as S
+from .sx import SX
+
+_INFIX = {"add": "+", "sub": "-", "mul": "*", "div": "/"}
+_CALL1 = {"exp": "exp", "log": "log", "sqrt": "sqrt", "sin": "sin", "cos": "cos", "tan": "tan",
+          "tanh": "tanh", "fabs": "fabs", "asin": "asin", "acos": "acos", "atan": "atan",
+          "sinh": "sinh", "cosh": "cosh"}
+_CMP = {"lt": "<", "le": "<=", "eq": "==", "ne": "!="}
+
+
+def _lit(v: float) -> str:
+    if math.isinf(v):
+        return "INFINITY" if v > 0 else "(-INFINITY)"
+    if math.isnan(v):
+        return "NAN"
+    r = repr(float(v))
+    return "(%s)" % r if v < 0 else r
+
+
+class CFunction:
+    """One generated function: name, ordered pointer arguments, body text, op statistics."""
+
+    def __init__(self, name: str, inputs: Sequence[Tuple[str, SX]], outputs: Sequence[Tuple[str, SX]],
+                 skip_zero_outputs: bool = False):
+        self.name = name
+        self.inputs = [(n, v if isinstance(v, SX) else SX(v)) for n, v in inputs]
+        self.outputs = [(n, v if isinstance(v, SX) else SX(v)) for n, v in outputs]
+        for n, v in self.inputs:
+            if not v.is_symbolic():
+                raise ValueError("%s: input %s is not purely symbolic" % (name, n))
+        self.skip_zero_outputs = skip_zero_outputs
+        self._flat_out = [e for _, o in self.outputs for e in o.elements()]
+        self.counts = S.op_counts(self._flat_out)
+        self.flops = int(sum(self.counts.values()))
+
+    # -- text ------------------------------------------------------------------
+    def signature(self, qualifier="MPCB_FN") -> str:
+        args = ["const double* %s" % n for n, _ in self.inputs] + ["double* %s" % n for n, _ in self.outputs]
+        return "%s void %s(%s)" % (qualifier, self.name, ", ".join(args))
+
+    def source(self, qualifier="MPCB_FN") -> str:
+        ref: Dict[int, str] = {}
+        lines: List[str] = []
+        known = set()
+        for name, var in self.inputs:
+            for i, e in enumerate(var.elements()):
+                ref[e.uid] = "%s[%d]" % (name, i)
+                known.add(e.uid)
+        order = S.topo_order(self._flat_out)
+        # count uses so that single-use cheap nodes could be inlined; keep it simple: one temp per node
+        used_inputs = set()
+        tcount = 0
+        for n in order:
+            if n.op == "sym":
+                if n.uid not in known:
+                    raise ValueError("%s: free symbol %s" % (self.name, n.val))
+                used_inputs.add(n.uid)
+                continue
+            if n.op == "const":
+                ref[n.uid] = _lit(n.val)
+                continue
+            a = [ref[c.uid] for c in n.args]
+            op = n.op
+            if op in _INFIX:
+                rhs = "%s %s %s" % (a[0], _INFIX[op], a[1])
+            elif op == "neg":
+                rhs = "-%s" % a[0]
+            elif op == "sq":
+                rhs = "%s * %s" % (a[0], a[0])
+            elif op in _CALL1:
+                rhs = "%s(%s)" % (_CALL1[op], a[0])
+            elif op == "sign":
+                rhs = "(double)((%s > 0.0) - (%s < 0.0))" % (a[0], a[0])
+            elif op == "not":
+                rhs = "(%s == 0.0) ? 1.0 : 0.0" % a[0]
+            elif op in _CMP:
+                rhs = "(%s %s %s) ? 1.0 : 0.0" % (a[0], _CMP[op], a[1])
+            elif op == "and":
+                rhs = "(%s != 0.0 && %s != 0.0) ? 1.0 : 0.0" % (a[0], a[1])
+            elif op == "or":
+                rhs = "(%s != 0.0 || %s != 0.0) ? 1.0 : 0.0" % (a[0], a[1])
+            elif op == "fmin":
+                rhs = "fmin(%s, %s)" % (a[0], a[1])
+            elif op == "fmax":
+                rhs = "fmax(%s, %s)" % (a[0], a[1])
+            elif op == "atan2":
+                rhs = "atan2(%s, %s)" % (a[0], a[1])
+            elif op == "pow":
+                b = n.args[1]
+                if b.op == "const" and float(b.val).is_integer() and 0 < abs(b.val) <= 8:
+                    k = int(abs(b.val))
+                    prod = " * ".join([a[0]] * k)
+                    rhs = prod if b.val > 0 else "1.0 / (%s)" % prod
+                else:
+                    rhs = "pow(%s, %s)" % (a[0], a[1])
+            elif op == "if_else":
+                rhs = "(%s != 0.0) ? %s : %s" % (a[0], a[1], a[2])
+            else:
+                raise NotImplementedError(op)
+            name = "w%d" % tcount
+            tcount += 1
+            lines.append("  const double %s = %s;" % (name, rhs))
+            ref[n.uid] = name
+        for name, var in self.outputs:
+            for i, e in enumerate(var.elements()):
+                if self.skip_zero_outputs and e is S.ZERO:
+                    continue
+                lines.append("  %s[%d] = %s;" % (name, i, ref[e.uid]))
+        unused = [n for n, v in self.inputs if not any(e.uid in used_inputs for e in v.elements())]
+        head = self.signature(qualifier) + " {"
+        voids = ["  (void)%s;" % n for n in unused]
+        return "\n".join([head] + voids + lines + ["}"]) + "\n"
+
+
+def emit_header(guard: str, defines: Dict[str, object], functions: Sequence[CFunction], preamble: str = "") -> str:
+    """A self-contained header: size/flag macros followed by the generated functions."""
+    out = ["// GENERATED by mpc_code_b200.codegen - do not edit.",
+           "#ifndef %s" % guard, "#define %s" % guard,
+           "#include <math.h>",
+           "#ifndef MPCB_FN",
+           "#  ifdef __CUDACC__",
+           "#    define MPCB_FN static __device__ __forceinline__",
+           "#  else",
+           "#    define MPCB_FN static inline",
+           "#  endif",
+           "#endif", ""]
+    if preamble:
+        out.append(preamble)
+    for k, v in defines.items():
+        if isinstance(v, bool):
+            v = int(v)
+        if isinstance(v, float):
+            v = _lit(v)
+        out.append("#define %s %s" % (k, v))
+    out.append("")
+    for f in functions:
+        out.append(f.source())
+    out.append("#endif")
+    return "\n".join(out) + "\n"
+
+
+# ----------------------------------------------------------------------------
+# host-side compilation of generated C (used by tests and by the CPU oracle; the
+# product path compiles the same text with nvcc inside the CUDA library instead)
+# ----------------------------------------------------------------------------
+
+class CModule:
+    """Generated functions compiled with gcc into a shared object and wrapped with ctypes/numpy."""
+
+    def __init__(self, name: str, functions: Sequence[CFunction], build_dir: str, cflags=("-O2",)):
+        import ctypes
+        import hashlib
+        import os
+        import subprocess
+        import numpy as np
+        self._np = np
+        self._ct = ctypes
+        self.functions = {f.name: f for f in functions}
+        src = emit_header("MPCB_GEN_%s_H" % name.upper(), {}, functions,
+                          preamble="#undef MPCB_FN\n#define MPCB_FN __attribute__((visibility(\"default\")))\n")
+        digest = hashlib.sha256((src + " ".join(cflags)).encode()).hexdigest()[:16]
+        os.makedirs(build_dir, exist_ok=True)
+        c_path = os.path.join(build_dir, "%s_%s.c" % (name, digest))
+        so_path = os.path.join(build_dir, "%s_%s.so" % (name, digest))
+        if not os.path.exists(so_path):
+            with open(c_path, "w") as fh:
+                fh.write(src)
+            tmp = so_path + ".tmp%d" % os.getpid()
+            subprocess.run(["gcc", "-shared", "-fPIC", "-std=c99", *cflags, "-o", tmp, c_path, "-lm"], check=True)
+            os.replace(tmp, so_path)
+        self.so_path = so_path
+        self._lib = ctypes.CDLL(so_path)
+        self._dp = ctypes.POINTER(ctypes.c_double)
+
+    def __getattr__(self, fname):
+        if fname.startswith("_") or fname not in self.functions:
+            raise AttributeError(fname)
+        f = self.functions[fname]
+        np, ct = self._np, self._ct
+        cfun = getattr(self._lib, fname)
+        cfun.restype = None
+        in_sizes = [v.numel() for _, v in f.inputs]
+        out_shapes = [v.shape for _, v in f.outputs]
+        dp = self._dp
+
+        def call(*args):
+            if len(args) != len(in_sizes):
+                raise TypeError("%s expects %d inputs" % (fname, len(in_sizes)))
+            ins = []
+            for a, n in zip(args, in_sizes):
+                arr = np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape(-1, order="F"))
+                if arr.size != n:
+                    raise ValueError("%s: input of size %d, expected %d" % (fname, arr.size, n))
+                ins.append(arr)
+            outs = [np.zeros(max(s[0] * s[1], 1)) for s in out_shapes]
+            cfun(*[a.ctypes.data_as(dp) for a in ins], *[o.ctypes.data_as(dp) for o in outs])
+            res = tuple(o[:s[0] * s[1]].reshape(s, order="F") for o, s in zip(outs, out_shapes))
+            return res[0] if len(res) == 1 else res
+        self.__dict__[fname] = call
+        return call
