@@ -132,7 +132,7 @@ def emit_header(guard: str, defines: Dict[str, object], functions: Sequence[CFun
            "#include <math.h>",
            "#ifndef MPCB_FN",
            "#  ifdef __CUDACC__",
-           "#    define MPCB_FN static __device__ __forceinline__",
+           "#    define MPCB_FN static __host__ __device__ __forceinline__",
            "#  else",
            "#    define MPCB_FN static inline",
            "#  endif",

@@ -1,0 +1,391 @@
+// mpcb_api.cu - kernels and the C ABI of include/mpcb.h for ONE compiled problem.
+//
+// Built per problem as  nvcc -gencode arch=compute_100a,code=sm_100a -I<dir with mpcb_model.h> ...
+// The generated mpcb_model.h carries the sizes and the user's model as __device__ functions.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include "mpcb.h"
+#include "mpcb_target.cuh"
+
+#ifndef MPCB_FLOPS_TABLE
+#define MPCB_FLOPS_TABLE
+#endif
+
+// ---------------------------------------------------------------------------------------------
+// kernels (thin wrappers; the arithmetic lives in the host/device functions of the .cuh files)
+// ---------------------------------------------------------------------------------------------
+#if MPCB_HAS_OCP
+struct OcpArgs {
+    int B;
+    const double* par; double* w; double* ws; InstState* st;
+    OcpShared S;
+};
+
+__device__ __forceinline__ OcpInst ocp_view(const OcpArgs& a, int inst) {
+    return ocp_inst(a.ws + (size_t)inst * OcpLayout::total, a.w + (size_t)inst * NW, a.par + (size_t)inst * NPAR, a.st + inst);
+}
+
+__global__ void __launch_bounds__(128) k_ocp_init(OcpArgs a) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int inst = tid / (NH + 1), k = tid % (NH + 1);
+    if (inst >= a.B) return;
+    OcpInst I = ocp_view(a, inst);
+    ocp_init_stage(I, a.S, k);
+}
+
+__global__ void __launch_bounds__(128) k_ocp_eval(OcpArgs a) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int inst = tid / NH, k = tid % NH;
+    if (inst >= a.B) return;
+    if (a.st[inst].state != ST_EVAL) return;
+    OcpInst I = ocp_view(a, inst);
+    ocp_eval_stage(I, a.S, k);
+}
+
+__global__ void __launch_bounds__(128) k_ocp_kkt(OcpArgs a) {
+    const int inst = blockIdx.x * blockDim.x + threadIdx.x;
+    if (inst >= a.B) return;
+    if (a.st[inst].state != ST_EVAL) return;
+    OcpInst I = ocp_view(a, inst);
+    ocp_kkt(I, a.S);
+}
+
+__global__ void __launch_bounds__(128) k_ocp_trial(OcpArgs a) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int inst = tid / NH, k = tid % NH;
+    if (inst >= a.B) return;
+    if (a.st[inst].state != ST_LS) return;
+    OcpInst I = ocp_view(a, inst);
+    ocp_trial_stage(I, a.S, k);
+}
+
+__global__ void __launch_bounds__(128) k_ocp_accept(OcpArgs a, int* n_active) {
+    const int inst = blockIdx.x * blockDim.x + threadIdx.x;
+    if (inst >= a.B) return;
+    if (a.st[inst].state == ST_LS) {
+        OcpInst I = ocp_view(a, inst);
+        ocp_accept(I, a.S);
+    }
+    if (a.st[inst].state != ST_DONE) atomicAdd(n_active, 1);
+}
+
+__global__ void k_ocp_output(OcpArgs a, double* f, int* status, int* iters) {
+    const int inst = blockIdx.x * blockDim.x + threadIdx.x;
+    if (inst >= a.B) return;
+    f[inst] = a.st[inst].fval; status[inst] = a.st[inst].status; iters[inst] = a.st[inst].iter;
+}
+
+// stage derivatives alone (mpcb_stage_derivs)
+__global__ void __launch_bounds__(128) k_stage_derivs(int B, const double* par, const double* w, const double* lam,
+                                                      double* A, double* Bm, double* c, double* H) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int inst = tid / NH, k = tid % NH;
+    if (inst >= B) return;
+    const double* wi = w + (size_t)inst * NW; const double* pi = par + (size_t)inst * NPAR;
+    double x[NX], u[NU], l[NX], d[ND + 1], px[NPX + 1], py[NPY + 1], t0;
+    for (int i = 0; i < NX; ++i) { x[i] = wi[k * NZ + i]; l[i] = lam[((size_t)inst * NH + k) * NX + i]; }
+    for (int i = 0; i < NU; ++i) u[i] = wi[k * NZ + NX + i];
+    stage_params(pi, k, d, px, py, &t0);
+    double xn[NX], Al[NX * NX], Bl[NX * NU], Hp[NZP];
+    for (int i = 0; i < NZP; ++i) Hp[i] = 0.0;
+    dyn_full(x, u, d, px, t0, l, xn, Al, Bl, Hp);
+    const size_t s = (size_t)inst * NH + k;
+    for (int i = 0; i < NX * NX; ++i) A[s * NX * NX + i] = Al[i];
+    for (int i = 0; i < NX * NU; ++i) Bm[s * NX * NU + i] = Bl[i];
+    for (int i = 0; i < NX; ++i) c[s * NX + i] = xn[i] - wi[(k + 1) * NZ + i];
+    for (int i = 0; i < NZP; ++i) H[s * NZP + i] = Hp[i];
+}
+#endif
+
+#if MPCB_HAS_TARGET
+__global__ void __launch_bounds__(64) k_target(int B, const double* par, double* w, double* f, int* status, int* iters,
+                                               TgtShared S) {
+    const int inst = blockIdx.x * blockDim.x + threadIdx.x;
+    if (inst >= B) return;
+    tgt_solve(par + (size_t)inst * MPCB_NPARSS, w + (size_t)inst * NWS, f + inst, status + inst, iters + inst, S);
+}
+#endif
+
+__global__ void __launch_bounds__(64) k_estimate(int B, int est_type, const double* y, const double* u, const double* t,
+                                                 const double* px, const double* py, double* xi, double* P, EstShared E) {
+    const int inst = blockIdx.x * blockDim.x + threadIdx.x;
+    if (inst >= B) return;
+    est_update(est_type, y + (size_t)inst * NY, u + (size_t)inst * NU, t[inst], px + (size_t)inst * NPX,
+               py + (size_t)inst * NPY, xi + (size_t)inst * NXI, P + (size_t)inst * NXI * NXI, E);
+}
+
+__global__ void k_model_output(int B, const double* x, const double* u, const double* d, const double* t,
+                               const double* py, double* y) {
+    const int inst = blockIdx.x * blockDim.x + threadIdx.x;
+    if (inst >= B) return;
+    double xl[NX], ul[NU], dl[ND + 1], pl[NPY + 1], yl[NY], tt = t[inst];
+    for (int i = 0; i < NX; ++i) xl[i] = x[(size_t)inst * NX + i];
+    for (int i = 0; i < NU; ++i) ul[i] = u[(size_t)inst * NU + i];
+    for (int i = 0; i < ND; ++i) dl[i] = d[(size_t)inst * ND + i];
+    for (int i = 0; i < NPY; ++i) pl[i] = py[(size_t)inst * NPY + i];
+    mdl_fy(xl, ul, dl, &tt, pl, yl);
+    for (int i = 0; i < NY; ++i) y[(size_t)inst * NY + i] = yl[i];
+}
+
+__global__ void k_model_step(int B, const double* x, const double* u, const double* d, const double* t,
+                             const double* px, double* xn) {
+    const int inst = blockIdx.x * blockDim.x + threadIdx.x;
+    if (inst >= B) return;
+    double xl[NX], ul[NU], dl[ND + 1], pl[NPX + 1], xo[NX];
+    for (int i = 0; i < NX; ++i) xl[i] = x[(size_t)inst * NX + i];
+    for (int i = 0; i < NU; ++i) ul[i] = u[(size_t)inst * NU + i];
+    for (int i = 0; i < ND; ++i) dl[i] = d[(size_t)inst * ND + i];
+    for (int i = 0; i < NPX; ++i) pl[i] = px[(size_t)inst * NPX + i];
+    dyn_value(xl, ul, dl, pl, t[inst], xo);
+    for (int i = 0; i < NX; ++i) xn[(size_t)inst * NX + i] = xo[i];
+}
+
+#if !MPCB_PLANT_NOMINAL
+__global__ void k_plant_meas(int B, const double* x, const double* u, const double* t, const double* pyp,
+                             const double* pymp, const double* noise, double* y) {
+    const int inst = blockIdx.x * blockDim.x + threadIdx.x;
+    if (inst >= B) return;
+    double yl[NY];
+    plant_meas(x + (size_t)inst * MPCB_NXP, u + (size_t)inst * NU, t[inst], pyp + (size_t)inst * MPCB_NPYP,
+               pymp + (size_t)inst * MPCB_NPYP, yl);
+    for (int i = 0; i < NY; ++i) y[(size_t)inst * NY + i] = yl[i] + (noise ? noise[(size_t)inst * NY + i] : 0.0);
+}
+__global__ void k_plant_step(int B, double* x, const double* u, const double* t, const double* pxp, const double* pxmp) {
+    const int inst = blockIdx.x * blockDim.x + threadIdx.x;
+    if (inst >= B) return;
+    plant_step(x + (size_t)inst * MPCB_NXP, u + (size_t)inst * NU, t[inst], pxp + (size_t)inst * MPCB_NPXP,
+               pxmp + (size_t)inst * MPCB_NPXP);
+}
+#endif
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+struct mpcb_ctx {
+    int B, device;
+    mpcb_opts_t opts_ss, opts_dyn;
+    std::string err;
+    double *ws, *lbx, *ubx, *lbg, *ubg, *ss_lbx, *ss_ubx, *Qkf, *Rkf, *Kest, *dmin, *dmax;
+    InstState* st;
+    int* n_active; int* h_active;
+    int have_dbounds, last_launches, last_ticks;
+};
+
+static IpmOpts to_ipm(const mpcb_opts_t& o) {
+    IpmOpts r;
+    r.max_iter = o.max_iter; r.tol = o.tol; r.mu_init = o.mu_init; r.bound_relax = o.bound_relax_factor;
+    r.bound_push = o.bound_push; r.acceptable_tol = o.acceptable_tol;
+    r.honor_original_bounds = o.honor_original_bounds; r.acceptable_iter = o.acceptable_iter;
+    return r;
+}
+
+static int fail(mpcb_ctx* h, const char* what, cudaError_t e) {
+    if (h) h->err = std::string(what) + ": " + cudaGetErrorString(e);
+    return -1;
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(h, #call, e_); } while (0)
+
+extern "C" {
+
+int mpcb_abi_version(void) { return MPCB_ABI_VERSION; }
+
+void mpcb_default_opts(mpcb_opts_t* o) {
+    o->max_iter = 100; o->tol = 1e-8; o->mu_init = 0.1; o->bound_relax_factor = 1e-8;
+    o->honor_original_bounds = 0; o->bound_push = 1e-2; o->acceptable_tol = 1e-6; o->acceptable_iter = 15;
+}
+
+int mpcb_get_dims(mpcb_dims_t* d) {
+    memset(d, 0, sizeof(*d));
+    d->nx = NX; d->nu = NU; d->ny = NY; d->nd = ND; d->npx = NPX; d->npy = NPY;
+    d->nxp = MPCB_NXP; d->npxp = MPCB_NPXP; d->npyp = MPCB_NPYP; d->nxi = NXI; d->N = NH; d->Mx = MX;
+#if MPCB_HAS_OCP
+    d->nw = NW; d->npar = NPAR; d->ng = NG; d->has_ocp = 1;
+#endif
+#if MPCB_HAS_TARGET
+    d->nwss = NWS; d->nparss = MPCB_NPARSS; d->has_target = 1;
+#endif
+    return 0;
+}
+
+long mpcb_model_flops(const char* name) {
+    static const struct { const char* n; long f; } table[] = { MPCB_FLOPS_TABLE {nullptr, 0} };
+    for (int i = 0; table[i].n; ++i) if (!strcmp(table[i].n, name)) return table[i].f;
+    return -1;
+}
+
+int mpcb_create(int batch, const mpcb_opts_t* oss, const mpcb_opts_t* odyn, mpcb_handle_t* out) {
+    mpcb_ctx* h = new mpcb_ctx();
+    h->B = batch; h->have_dbounds = 0; h->last_launches = 0; h->last_ticks = 0;
+    mpcb_default_opts(&h->opts_ss); mpcb_default_opts(&h->opts_dyn);
+    if (oss) h->opts_ss = *oss;
+    if (odyn) h->opts_dyn = *odyn;
+    *out = h;
+    if (batch <= 0) { h->err = "batch must be positive"; return -2; }
+    CK(cudaGetDevice(&h->device));
+    h->ws = nullptr; h->st = nullptr; h->lbx = h->ubx = h->lbg = h->ubg = nullptr;
+#if MPCB_HAS_OCP
+    CK(cudaMalloc(&h->ws, sizeof(double) * (size_t)batch * OcpLayout::total));
+    CK(cudaMemset(h->ws, 0, sizeof(double) * (size_t)batch * OcpLayout::total));
+    CK(cudaMalloc(&h->st, sizeof(InstState) * (size_t)batch));
+    CK(cudaMalloc(&h->lbx, sizeof(double) * NW)); CK(cudaMalloc(&h->ubx, sizeof(double) * NW));
+    CK(cudaMalloc(&h->lbg, sizeof(double) * (NH * NGS))); CK(cudaMalloc(&h->ubg, sizeof(double) * (NH * NGS)));
+#endif
+    h->ss_lbx = h->ss_ubx = nullptr;
+#if MPCB_HAS_TARGET
+    CK(cudaMalloc(&h->ss_lbx, sizeof(double) * NWS)); CK(cudaMalloc(&h->ss_ubx, sizeof(double) * NWS));
+#endif
+    CK(cudaMalloc(&h->Qkf, sizeof(double) * NXI * NXI)); CK(cudaMalloc(&h->Rkf, sizeof(double) * NY * NY));
+    CK(cudaMalloc(&h->Kest, sizeof(double) * NXI * NY));
+    CK(cudaMalloc(&h->dmin, sizeof(double) * (ND + 1))); CK(cudaMalloc(&h->dmax, sizeof(double) * (ND + 1)));
+    CK(cudaMemset(h->Qkf, 0, sizeof(double) * NXI * NXI)); CK(cudaMemset(h->Rkf, 0, sizeof(double) * NY * NY));
+    CK(cudaMemset(h->Kest, 0, sizeof(double) * NXI * NY));
+    CK(cudaMalloc(&h->n_active, sizeof(int)));
+    CK(cudaMallocHost(&h->h_active, sizeof(int)));
+    return 0;
+}
+
+int mpcb_destroy(mpcb_handle_t h) {
+    if (!h) return 0;
+    cudaFree(h->ws); cudaFree(h->st); cudaFree(h->lbx); cudaFree(h->ubx); cudaFree(h->lbg); cudaFree(h->ubg);
+    cudaFree(h->ss_lbx); cudaFree(h->ss_ubx); cudaFree(h->Qkf); cudaFree(h->Rkf); cudaFree(h->Kest);
+    cudaFree(h->dmin); cudaFree(h->dmax); cudaFree(h->n_active); cudaFreeHost(h->h_active);
+    delete h;
+    return 0;
+}
+
+const char* mpcb_last_error(mpcb_handle_t h) { return h ? h->err.c_str() : "null handle"; }
+
+int mpcb_set_const(mpcb_handle_t h, const char* name, const double* p, int n) {
+    struct { const char* nm; double* dst; int len; } tab[] = {
+#if MPCB_HAS_OCP
+        {"ocp_lbx", h->lbx, NW}, {"ocp_ubx", h->ubx, NW}, {"ocp_lbg", h->lbg, NH * NG}, {"ocp_ubg", h->ubg, NH * NG},
+#endif
+#if MPCB_HAS_TARGET
+        {"ss_lbx", h->ss_lbx, NWS}, {"ss_ubx", h->ss_ubx, NWS},
+#endif
+        {"Q_kf", h->Qkf, NXI * NXI}, {"R_kf", h->Rkf, NY * NY}, {"K_est", h->Kest, NXI * NY},
+        {"dmin", h->dmin, ND}, {"dmax", h->dmax, ND},
+    };
+    for (auto& e : tab) {
+        if (strcmp(e.nm, name)) continue;
+        if (n != e.len) { h->err = std::string("mpcb_set_const: wrong length for ") + name; return -2; }
+        if (n > 0) CK(cudaMemcpy(e.dst, p, sizeof(double) * n, cudaMemcpyHostToDevice));
+        if (!strcmp(name, "dmax")) h->have_dbounds = 1;
+        return 0;
+    }
+    h->err = std::string("mpcb_set_const: unknown name ") + name;
+    return -2;
+}
+
+static inline int nblk(long n, int bs) { return (int)((n + bs - 1) / bs); }
+
+int mpcb_ocp(mpcb_handle_t h, const double* par, double* w, double* f, int* status, int* iters, void* stream) {
+#if MPCB_HAS_OCP
+    cudaStream_t s = (cudaStream_t)stream;
+    OcpArgs a;
+    a.B = h->B; a.par = par; a.w = w; a.ws = h->ws; a.st = h->st;
+    a.S.lbx = h->lbx; a.S.ubx = h->ubx; a.S.lbg = h->lbg; a.S.ubg = h->ubg; a.S.o = to_ipm(h->opts_dyn);
+    const int bs = 128;
+    const long nst = (long)h->B * NH;
+    int launches = 0, ticks = 0;
+    k_ocp_init<<<nblk((long)h->B * (NH + 1), bs), bs, 0, s>>>(a); launches++;
+    // every instance needs at most max_iter+1 evaluations plus its line-search backtracks
+    const int max_ticks = (h->opts_dyn.max_iter + 2) * 8;
+    const int check_every = 2;
+    while (ticks < max_ticks) {
+        for (int c = 0; c < check_every; ++c) {
+            k_ocp_eval<<<nblk(nst, bs), bs, 0, s>>>(a);
+            k_ocp_kkt<<<nblk(h->B, 64), 64, 0, s>>>(a);
+            k_ocp_trial<<<nblk(nst, bs), bs, 0, s>>>(a);
+            if (c == check_every - 1) CK(cudaMemsetAsync(h->n_active, 0, sizeof(int), s));
+            k_ocp_accept<<<nblk(h->B, 64), 64, 0, s>>>(a, h->n_active);
+            launches += 4; ticks++;
+        }
+        CK(cudaMemcpyAsync(h->h_active, h->n_active, sizeof(int), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        if (*h->h_active == 0) break;
+    }
+    k_ocp_output<<<nblk(h->B, 128), 128, 0, s>>>(a, f, status, iters); launches++;
+    CK(cudaGetLastError());
+    h->last_launches = launches; h->last_ticks = ticks;
+    return 0;
+#else
+    h->err = "library built without the OCP"; return -3;
+#endif
+}
+
+int mpcb_stage_derivs(mpcb_handle_t h, const double* par, const double* w, const double* lam,
+                      double* A, double* Bm, double* c, double* H, void* stream) {
+#if MPCB_HAS_OCP
+    k_stage_derivs<<<nblk((long)h->B * NH, 128), 128, 0, (cudaStream_t)stream>>>(h->B, par, w, lam, A, Bm, c, H);
+    CK(cudaGetLastError());
+    h->last_launches = 1;
+    return 0;
+#else
+    h->err = "library built without the OCP"; return -3;
+#endif
+}
+
+int mpcb_target(mpcb_handle_t h, const double* par_ss, double* wss, double* fss, int* status, int* iters, void* stream) {
+#if MPCB_HAS_TARGET
+    TgtShared S; S.lbx = h->ss_lbx; S.ubx = h->ss_ubx; S.o = to_ipm(h->opts_ss);
+    k_target<<<nblk(h->B, 64), 64, 0, (cudaStream_t)stream>>>(h->B, par_ss, wss, fss, status, iters, S);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    h->last_launches = 1; h->last_ticks = 1;
+    return 0;
+#else
+    h->err = "library built without the target problem"; return -3;
+#endif
+}
+
+int mpcb_estimate(mpcb_handle_t h, int est_type, const double* y, const double* u, const double* t, const double* px,
+                  const double* py, double* xi, double* P, void* stream) {
+    EstShared E; E.Q = h->Qkf; E.R = h->Rkf; E.K = h->Kest; E.dmin = h->dmin; E.dmax = h->dmax; E.has_dbounds = h->have_dbounds;
+    k_estimate<<<nblk(h->B, 64), 64, 0, (cudaStream_t)stream>>>(h->B, est_type, y, u, t, px, py, xi, P, E);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int mpcb_model_output(mpcb_handle_t h, const double* x, const double* u, const double* d, const double* t,
+                      const double* py, double* y, void* stream) {
+    k_model_output<<<nblk(h->B, 128), 128, 0, (cudaStream_t)stream>>>(h->B, x, u, d, t, py, y);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int mpcb_model_step(mpcb_handle_t h, const double* x, const double* u, const double* d, const double* t,
+                    const double* px, double* xn, void* stream) {
+    k_model_step<<<nblk(h->B, 128), 128, 0, (cudaStream_t)stream>>>(h->B, x, u, d, t, px, xn);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int mpcb_plant_meas(mpcb_handle_t h, const double* x, const double* u, const double* t, const double* pyp,
+                    const double* pymp, const double* noise, double* y, void* stream) {
+#if !MPCB_PLANT_NOMINAL
+    k_plant_meas<<<nblk(h->B, 128), 128, 0, (cudaStream_t)stream>>>(h->B, x, u, t, pyp, pymp, noise, y);
+    CK(cudaGetLastError());
+    return 0;
+#else
+    h->err = "nominal plant: use mpcb_model_output (MPC_code.py:531-532)"; return -3;
+#endif
+}
+
+int mpcb_plant_step(mpcb_handle_t h, double* x, const double* u, const double* t, const double* pxp,
+                    const double* pxmp, void* stream) {
+#if !MPCB_PLANT_NOMINAL
+    k_plant_step<<<nblk(h->B, 128), 128, 0, (cudaStream_t)stream>>>(h->B, x, u, t, pxp, pxmp);
+    CK(cudaGetLastError());
+    return 0;
+#else
+    h->err = "nominal plant: use mpcb_model_step (MPC_code.py:813-814)"; return -3;
+#endif
+}
+
+int mpcb_last_launches(mpcb_handle_t h) { return h->last_launches; }
+int mpcb_last_ticks(mpcb_handle_t h) { return h->last_ticks; }
+
+}  // extern "C"

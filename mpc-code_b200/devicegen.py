@@ -1,0 +1,193 @@
+"""Generate the per-problem device header (``mpcb_model.h``) consumed by ``csrc/mpcb_kernels.cu``.
+
+The reference hands CasADi whole-NLP graphs and lets its VM evaluate them (``Control_Calc.py:256-258``).
+Here the user's maps are emitted as small ``__device__`` functions - the continuous right-hand side
+with its sensitivity / adjoint / second-order products, the output map, the stage and terminal
+costs, the target problem's pieces, the plant - and the hand-written kernels orchestrate them
+(RK4 sub-stepping, Riccati recursion, line search).  Matrix products that involve model Jacobians
+are generated *symbolically* (e.g. ``K = f_x S + [0|f_u]``) so structural zeros cost nothing.
+
+Layouts: matrices are column-major; symmetric matrices are packed lower-triangular row-wise
+(``idx(i,j) = i(i+1)/2 + j``, ``j <= i``).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import numpy as np
+
+from . import symbolic as S
+from .codegen import CFunction, emit_header
+from .sx import SX, Function, gradient, hessian, jacobian, mtimes, vertcat, horzcat
+
+
+def tril_pack(H: SX) -> SX:
+    n = H.size1()
+    return SX([H[i, j]._as_scalar_expr() for i in range(n) for j in range(i + 1)]) if n else SX()
+
+
+def _depends_on(expr: SX, var: SX) -> bool:
+    ids = {e.uid for e in var.elements()}
+    return any(s.uid in ids for s in S.symbols_of(expr.elements()))
+
+
+def _rhs_functions(prefix: str, rhs: Function, nx: int, nu: int, nd: int, npx: int, nxi: int) -> List[CFunction]:
+    """Right-hand side ``f(x,u,d,t,px)`` with the products the RK4 sweeps need."""
+    x, u, d, t, px = [SX.sym(n, k) for n, k in (("x", nx), ("u", nu), ("d", nd), ("t", 1), ("px", npx))]
+    f = rhs(x, u, d, t, px)
+    base = [("x", x), ("u", u), ("d", d), ("t", t), ("px", px)]
+    fns = [CFunction(prefix + "f", base, [("xdot", f)])]
+    nu_adj = SX.sym("nu", nx)
+    nuf = mtimes(nu_adj.T, f)
+    fns.append(CFunction(prefix + "f_vjp", base + [("nu", nu_adj)], [("fxTnu", gradient(nuf, x))]))
+    fx = jacobian(f, x)
+    # sensitivities with respect to (x0, u)
+    nz = nx + nu
+    Sxu = SX.sym("S", nx, nz)
+    fu = jacobian(f, u)
+    K = mtimes(fx, Sxu) + horzcat(SX.zeros(nx, nx), fu)
+    fns.append(CFunction(prefix + "f_s", base + [("S", Sxu)], [("xdot", f), ("K", K)]))
+    zz = vertcat(x, u)
+    Hf, _ = hessian(nuf, zz)
+    dZ = vertcat(Sxu, horzcat(SX.zeros(nu, nx), SX.eye(nu)))
+    Hc = mtimes(dZ.T, mtimes(Hf, dZ))
+    fns.append(CFunction(prefix + "f_sh", base + [("S", Sxu), ("nu", nu_adj)],
+                         [("xdot", f), ("K", K), ("Hc", tril_pack(Hc))]))
+    # sensitivities with respect to xi = (x0[, d]) for the estimator
+    Sxi = SX.sym("S", nx, nxi)
+    Kd = mtimes(fx, Sxi)
+    if nxi > nx:
+        Kd = Kd + horzcat(SX.zeros(nx, nx), jacobian(f, d))
+    fns.append(CFunction(prefix + "f_s_xi", base + [("S", Sxi)], [("xdot", f), ("K", Kd)]))
+    return fns
+
+
+def _discrete_functions(prefix: str, Fx_model: Function, nx, nu, nd, npx, nxi) -> List[CFunction]:
+    x, u, d, t, px = [SX.sym(n, k) for n, k in (("x", nx), ("u", nu), ("d", nd), ("t", 1), ("px", npx))]
+    k = SX.sym("k", 1)
+    F = Fx_model(x, u, k, d, t, px)
+    if _depends_on(SX(F), k):
+        raise ValueError("a discrete/linear Fx_model must not depend on the integration step k")
+    base = [("x", x), ("u", u), ("d", d), ("t", t), ("px", px)]
+    lam = SX.sym("lam", nx)
+    zz = vertcat(x, u)
+    Hf, _ = hessian(mtimes(lam.T, F), zz)
+    fns = [CFunction(prefix + "F", base, [("xn", F)]),
+           CFunction(prefix + "F_d", base + [("lam", lam)],
+                     [("xn", F), ("A", jacobian(F, x)), ("B", jacobian(F, u)), ("Hc", tril_pack(Hf))])]
+    xi = vertcat(x, d) if nxi > nx else x
+    fns.append(CFunction(prefix + "F_xd", base, [("xn", F), ("Axd", jacobian(F, xi))]))
+    return fns
+
+
+def generate_header(prob, ss_spec, ocp_spec, opts: Optional[Dict] = None) -> Dict[str, object]:
+    """Return ``{"text": header_source, "defines": {...}, "flops": {...}}`` for one problem."""
+    nx, nu, ny, nd, npx, npy, N = prob.nx, prob.nu, prob.ny, prob.nd, prob.npx, prob.npy, prob.N
+    s = prob.sym
+    fns: List[CFunction] = []
+    D: Dict[str, object] = dict(MPCB_NX=nx, MPCB_NU=nu, MPCB_NY=ny, MPCB_ND=nd, MPCB_NPX=npx, MPCB_NPY=npy,
+                                MPCB_NXP=prob.nxp, MPCB_NPXP=prob.npxp, MPCB_NPYP=prob.npyp,
+                                MPCB_NH=N, MPCB_HSTEP=float(prob.h),
+                                MPCB_OFFREE=0 if prob.flags["offree"] == "no" else 1,
+                                MPCB_NXI=prob.nxi)
+    # ---- model maps -------------------------------------------------------
+    kind = prob.Fx_model.meta.get("kind")
+    if kind == "rk4":
+        D["MPCB_DYN_RK4"] = 1
+        D["MPCB_MX"] = int(prob.Fx_model.meta["substeps"])
+        fns += _rhs_functions("mdl_", prob.Fx_model.meta["rhs"], nx, nu, nd, npx, prob.nxi)
+        d_, px_ = SX.sym("d", nd), SX.sym("px", npx)
+        post = prob.Fx_model.meta["post"](d_, px_)
+        fns.append(CFunction("mdl_post", [("d", d_), ("px", px_)], [("post", post), ("Jd", jacobian(post, d_))]))
+    else:
+        D["MPCB_DYN_RK4"] = 0
+        D["MPCB_MX"] = 1
+        fns += _discrete_functions("mdl_", prob.Fx_model, nx, nu, nd, npx, prob.nxi)
+    x, u, d, t, py = s["x"], s["u"], s["d"], s["t"], s["py"]
+    Fy = prob.Fy_model(x, u, d, t, py)
+    base_y = [("x", x), ("u", u), ("d", d), ("t", t), ("py", py)]
+    xi = vertcat(x, d) if prob.flags["offree"] != "no" else x
+    fns.append(CFunction("mdl_fy", base_y, [("y", Fy)]))
+    fns.append(CFunction("mdl_fy_xi", base_y, [("y", Fy), ("C", jacobian(Fy, xi))]))
+
+    # ---- plant -------------------------------------------------------------
+    if prob.flags["Fp_nominal"] is True:
+        D["MPCB_PLANT_NOMINAL"] = 1
+        D["MPCB_PLANT_RK4"] = 0
+        D["MPCB_PMX"] = 1
+    else:
+        D["MPCB_PLANT_NOMINAL"] = 0
+        xp, pxp, pyp, pxmp, pymp, k = s["xp"], s["pxp"], s["pyp"], s["pxmp"], s["pymp"], s["k"]
+        pkind = prob.Fx_p.meta.get("kind")
+        if pkind == "rk4":
+            D["MPCB_PLANT_RK4"] = 1
+            D["MPCB_PMX"] = int(prob.Fx_p.meta["substeps"])
+            rhs_p = prob.Fx_p.meta["rhs"](xp, u, pxp, t, pxmp)
+            fns.append(CFunction("plt_f", [("x", xp), ("u", u), ("pxp", pxp), ("t", t), ("pxmp", pxmp)], [("xdot", rhs_p)]))
+            fns.append(CFunction("plt_post", [("pxp", pxp), ("pxmp", pxmp)], [("post", prob.Fx_p.meta["post"](pxp, pxmp))]))
+        else:
+            D["MPCB_PLANT_RK4"] = 0
+            D["MPCB_PMX"] = 1
+            Fp = prob.Fx_p(xp, u, pxp, t, k, pxmp)
+            if _depends_on(SX(Fp), k):
+                raise ValueError("a discrete/linear plant must not depend on the integration step k")
+            fns.append(CFunction("plt_F", [("x", xp), ("u", u), ("pxp", pxp), ("t", t), ("pxmp", pxmp)], [("xn", Fp)]))
+        fns.append(CFunction("plt_fy", [("x", xp), ("u", u), ("pyp", pyp), ("t", t), ("pymp", pymp)],
+                             [("y", prob.Fy_p(xp, u, pyp, t, pymp))]))
+
+    # ---- OCP stage maps (Control_Calc.py:124-210) ---------------------------
+    if ocp_spec is not None:
+        o = ocp_spec
+        if o.uses_uprev:
+            raise NotImplementedError("Delta-u costs / Delta-u bounds (DUForm, DUFormEcon, Dumin/Dumax) are not on the device path yet")
+        if o.flags["ContForm"] is True:
+            raise NotImplementedError("ContForm (integrated stage cost) is not on the device path yet")
+        if o.term_eq is not None:
+            raise NotImplementedError("TermCons (terminal equality) is not on the device path yet")
+        D.update(MPCB_HAS_OCP=1, MPCB_NW=o.nw, MPCB_NPAR=o.npar, MPCB_NG=(0 if o.yFree else o.p))
+        for k_, v_ in o.off.items():
+            D["MPCB_OFF_%s" % k_.upper()] = v_
+        X, U, Up, par, pxk, pyk = o.X, o.U, o.Uprev, o.par, o.pxk, o.pyk
+        zz = vertcat(X, U)
+        ins_c = [("X", X), ("U", U), ("par", par), ("pxk", pxk), ("pyk", pyk)]
+        Hc, gc = hessian(o.stage_cost, zz)
+        fns.append(CFunction("ocp_cost", ins_c, [("l", o.stage_cost)]))
+        fns.append(CFunction("ocp_cost_d", ins_c, [("l", o.stage_cost), ("g", gc), ("H", tril_pack(Hc))]))
+        Ht, gt = hessian(o.term_cost, o.XN)
+        fns.append(CFunction("ocp_term", [("XN", o.XN), ("par", par)], [("V", o.term_cost)]))
+        fns.append(CFunction("ocp_term_d", [("XN", o.XN), ("par", par)],
+                             [("V", o.term_cost), ("g", gt), ("H", tril_pack(Ht))]))
+        if not o.yFree:
+            mult = SX.sym("mult", o.p)
+            Hy, _ = hessian(mtimes(mult.T, o.Y), zz)
+            ins_y = [("X", X), ("U", U), ("par", par), ("pyk", pyk)]
+            fns.append(CFunction("ocp_out", ins_y, [("Y", o.Y)]))
+            fns.append(CFunction("ocp_out_d", ins_y + [("mult", mult)],
+                                 [("Y", o.Y), ("JY", jacobian(o.Y, zz)), ("HY", tril_pack(Hy))]))
+            D["MPCB_OUT_LINEAR"] = int(all(e is S.ZERO for e in Hy.elements()))
+    else:
+        D["MPCB_HAS_OCP"] = 0
+
+    # ---- target problem (Target_Calc.py:75-124) ------------------------------
+    if ss_spec is not None:
+        t_ = ss_spec
+        D.update(MPCB_HAS_TARGET=1, MPCB_NWSS=t_.nw, MPCB_NPARSS=t_.npar)
+        for k_, v_ in t_.off.items():
+            D["MPCB_OFFSS_%s" % k_.upper()] = v_
+        w, par = t_.wss, t_.par
+        Hf, gf = hessian(t_.cost, w)
+        fns.append(CFunction("tgt_cost", [("w", w), ("par", par)], [("f", t_.cost)]))
+        fns.append(CFunction("tgt_cost_d", [("w", w), ("par", par)], [("f", t_.cost), ("g", gf), ("H", tril_pack(Hf))]))
+        mult = SX.sym("mult", t_.p)
+        yres = t_.Ynext - t_.Ys
+        Hy, _ = hessian(mtimes(mult.T, yres), w)
+        fns.append(CFunction("tgt_out", [("w", w), ("par", par)], [("r", yres)]))
+        fns.append(CFunction("tgt_out_d", [("w", w), ("par", par), ("mult", mult)],
+                             [("r", yres), ("J", jacobian(yres, w)), ("H", tril_pack(Hy))]))
+    else:
+        D["MPCB_HAS_TARGET"] = 0
+
+    flops = {f.name: f.flops for f in fns}
+    table = " ".join('{"%s", %dL},' % (n, v) for n, v in flops.items())
+    text = emit_header("MPCB_MODEL_H", D, fns, preamble="#define MPCB_FLOPS_TABLE " + table)
+    return dict(text=text, defines=D, flops=flops, functions=fns)

@@ -76,6 +76,7 @@ class IpmOptions:
     delta_c_bar: float = 1e-8
     kappa_c: float = 0.25
     hessian_constant: bool = False
+    verbose: bool = False
 
 
 @dataclass
@@ -130,6 +131,35 @@ def solve_nlp(n: int, m: int, fun: Callable, x0, xL, xU, gL, gU, opts: Optional[
     xfull[fixed] = xL[fixed]
     eq = np.where(gL == gU)[0]
     ineq = np.where(gL != gU)[0]
+    # Equality rows that involve no free variable (the reference's `x0 - X[0]` row once X[0] is
+    # fixed through its bounds, Control_Calc.py:126 + MPC_code.py:734) are constants: IPOPT keeps
+    # them and regularises the singular row with delta_c; here they are checked and dropped.
+    if eq.size and free.size:
+        r0 = fun(xfull, np.zeros(m), 2)
+        J0 = np.asarray(r0["J"], dtype=float)[np.ix_(eq, free)]
+        const_rows = np.abs(J0).max(axis=1) == 0.0
+        if const_rows.any():
+            viol = np.abs(np.asarray(r0["g"], dtype=float)[eq[const_rows]] - gL[eq[const_rows]])
+            if viol.size and viol.max() > 1e-8:
+                return IpmResult(x=xfull.copy(), f=float(r0["f"]), status=2, iters=0, lam_g=np.zeros(m),
+                                 info=dict(reason="constant equality row violated"))
+            eq = eq[~const_rows]
+    # Range rows that involve no free variable (the reference's Y_0 row when the output map does not
+    # depend on u: its x is the fixed X[0], Control_Calc.py:128-151) cannot be influenced: if such a
+    # row lies outside its relaxed bounds the NLP is infeasible - IPOPT ends in restoration with
+    # Infeasible_Problem_Detected, which is the one status the reference loop acts on (MPC_code.py:786).
+    if ineq.size and free.size:
+        r0 = fun(xfull, np.zeros(m), 2)
+        Ji = np.asarray(r0["J"], dtype=float)[np.ix_(ineq, free)]
+        crow = np.abs(Ji).max(axis=1) == 0.0
+        if crow.any():
+            v = np.asarray(r0["g"], dtype=float)[ineq[crow]]
+            lo_c = gL[ineq[crow]]; hi_c = gU[ineq[crow]]
+            lo_c = np.where(np.isfinite(lo_c), lo_c - o.bound_relax_factor * np.maximum(1.0, np.abs(lo_c)), lo_c)
+            hi_c = np.where(np.isfinite(hi_c), hi_c + o.bound_relax_factor * np.maximum(1.0, np.abs(hi_c)), hi_c)
+            if np.any(v < lo_c - o.tol) or np.any(v > hi_c + o.tol):
+                return IpmResult(x=xfull.copy(), f=float(r0["f"]), status=2, iters=0, lam_g=np.zeros(m),
+                                 info=dict(reason="constant range row outside its bounds"))
     nf, me, mi = free.size, eq.size, ineq.size
     nv = nf + mi                       # primal variables: free x, then slacks
     mc = me + mi
@@ -291,8 +321,8 @@ def solve_nlp(n: int, m: int, fun: Callable, x0, xL, xU, gL, gU, opts: Optional[
         theta_min = 1e-4 * max(1.0, theta0); theta_max = 1e4 * max(1.0, theta0)
         gphi_d = float(ev["grad"] @ dv - mu * (dv / dL)[hasL].sum() + mu * (dv / dU)[hasU].sum())
         if gphi_d < 0 and theta <= theta_min:
-            a_min = min(o.gamma_theta, o.gamma_phi * theta / (-gphi_d) if theta > 0 else np.inf,
-                        o.delta * theta ** o.s_theta / (-gphi_d) ** o.s_phi if theta > 0 else np.inf)
+            a_min = min(o.gamma_theta, o.gamma_phi * theta / (-gphi_d),
+                        o.delta * theta ** o.s_theta / (-gphi_d) ** o.s_phi)
         elif gphi_d < 0:
             a_min = min(o.gamma_theta, o.gamma_phi * theta / (-gphi_d))
         else:
@@ -326,6 +356,9 @@ def solve_nlp(n: int, m: int, fun: Callable, x0, xL, xU, gL, gU, opts: Optional[
             if accepted:
                 break
             alpha *= 0.5
+        if o.verbose:
+            print("it %3d mu %.1e E0 %.2e theta %.3e phi %.8e gphid %.2e amax %.2e az %.2e alpha %.2e dw %.1e %s nfilt %d a_min %.1e"
+                  % (it, mu, E0, theta, phi, gphi_d, alpha_max, alpha_z, alpha, delta_w, "acc" if accepted else "REJ", len(filt), a_min))
         if not accepted:
             status = -2
             break

@@ -1,0 +1,128 @@
+import ctypes
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import mpc_code_b200  # noqa: E402,F401
+import __graft_entry__ as entry  # noqa: E402
+
+REFERENCE = "/root/reference"
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def pytest_collection_modifyitems(config, items):
+    try:
+        import torch
+        have_gpu = torch.cuda.is_available()
+    except Exception:
+        have_gpu = False
+    if have_gpu:
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+class Bundle:
+    """Problem + specs + oracle model + (lazily) the CPU harness / CUDA library of one example."""
+
+    def __init__(self, name):
+        from mpc_code_b200.build import build_library
+        self.name = name
+        self.prob, self.ss, self.ocp = entry._problem(name)
+        self._oracle = self._harness = self._lib = None
+        self._build_library = build_library
+
+    @property
+    def oracle(self):
+        if self._oracle is None:
+            from oracle import cmodel
+            self._oracle = cmodel.build(self.name, self.prob, self.ocp, self.ss)
+        return self._oracle
+
+    @property
+    def lib(self):
+        if self._lib is None:
+            self._lib = self._build_library(self.name, self.prob, self.ss, self.ocp)
+        return self._lib
+
+    @property
+    def harness(self):
+        if self._harness is None:
+            res = self.lib
+            path = os.path.join(os.path.dirname(res["so"]), "harness_%s_%s.so" % (self.name, res["digest"]))
+            if not os.path.exists(path):
+                entry.build_harness(os.path.dirname(res["header"]), path)
+            self._harness = ctypes.CDLL(path)
+        return self._harness
+
+    # ---- conveniences for the CSTR-style tests ---------------------------------
+    def ocp_par(self, xhat, xs, us, d, um1=None, t=0.0):
+        p = self.prob
+        um1 = p.u0 if um1 is None else um1
+        return np.concatenate([xhat, xs, us, d, um1, [t], np.zeros(p.ny * p.nu),
+                               np.zeros(p.npx * p.N), np.zeros(p.npy * p.N)])
+
+    def cold_guess(self):
+        p = self.prob
+        nxu = p.nx + p.nu
+        w = np.zeros(p.nw)
+        for k in range(p.N + 1):
+            w[nxu * k:nxu * k + p.nx] = p.x0_m
+        for k in range(p.N):
+            w[nxu * k + p.nx:nxu * (k + 1)] = p.u0
+        return w
+
+    def ocp_range_bounds(self):
+        o = self.ocp
+        n_dyn = o.n * (o.N + 1)
+        ny_rows = 0 if o.yFree else o.p * o.N
+        return (np.ascontiguousarray(o.g_lb[n_dyn:n_dyn + ny_rows]), np.ascontiguousarray(o.g_ub[n_dyn:n_dyn + ny_rows]))
+
+    def harness_ocp(self, par, w0, max_iter=100, tol=1e-8, mu_init=0.1, relax=1e-8, honor=0):
+        H = self.harness
+        par = np.ascontiguousarray(np.atleast_2d(par), dtype=float); w = np.ascontiguousarray(np.atleast_2d(w0), dtype=float).copy()
+        B = par.shape[0]
+        f = np.zeros(B); st = np.zeros(B, dtype=np.int32); it = np.zeros(B, dtype=np.int32); ticks = ctypes.c_int(0)
+        lbg, ubg = self.ocp_range_bounds()
+        if lbg.size == 0:
+            lbg = ubg = np.zeros(1)
+        lbx, ubx = np.ascontiguousarray(self.ocp.w_lb), np.ascontiguousarray(self.ocp.w_ub)
+        H.h_ocp.argtypes = [ctypes.c_int] + [ctypes.c_void_p] * 9 + [ctypes.c_int, ctypes.c_double, ctypes.c_double,
+                                                                     ctypes.c_double, ctypes.c_int, ctypes.c_void_p]
+        H.h_ocp(B, par.ctypes.data, w.ctypes.data, f.ctypes.data, st.ctypes.data, it.ctypes.data, lbx.ctypes.data,
+                ubx.ctypes.data, lbg.ctypes.data, ubg.ctypes.data, max_iter, tol, mu_init, relax, honor, ctypes.addressof(ticks))
+        return w, f, st, it, ticks.value
+
+    def harness_target(self, par, w0, max_iter=100):
+        H = self.harness
+        par = np.ascontiguousarray(np.atleast_2d(par), dtype=float); w = np.ascontiguousarray(np.atleast_2d(w0), dtype=float).copy()
+        B = par.shape[0]
+        f = np.zeros(B); st = np.zeros(B, dtype=np.int32); it = np.zeros(B, dtype=np.int32)
+        lbx, ubx = np.ascontiguousarray(self.ss.w_lb), np.ascontiguousarray(self.ss.w_ub)
+        H.h_target.argtypes = [ctypes.c_int] + [ctypes.c_void_p] * 7 + [ctypes.c_int, ctypes.c_double, ctypes.c_double,
+                                                                        ctypes.c_double, ctypes.c_int]
+        H.h_target(B, par.ctypes.data, w.ctypes.data, f.ctypes.data, st.ctypes.data, it.ctypes.data, lbx.ctypes.data,
+                   ubx.ctypes.data, max_iter, 1e-8, 0.1, 1e-8, 0)
+        return w, f, st, it
+
+
+_BUNDLES = {}
+
+
+@pytest.fixture(scope="session")
+def nmpc():
+    if "nmpc_cstr" not in _BUNDLES:
+        _BUNDLES["nmpc_cstr"] = Bundle("nmpc_cstr")
+    return _BUNDLES["nmpc_cstr"]

@@ -1,0 +1,158 @@
+"""Parity of the CUDA path (through the C ABI, include/mpcb.h) with the CPU oracle - run on the B200 box.
+
+Tolerances are the ones BASELINE.json states: optimal input trajectory <= 1e-6 abs, cost <= 1e-8 rel,
+same active set.  (Against the committed oracle fixtures the agreement is in fact ~1e-10.)
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+G = np.load(os.path.join(GOLDEN, "nmpc_oracle.npz"))
+U_TOL, F_RTOL = 1e-6, 1e-8
+
+
+@pytest.fixture(scope="module")
+def cp(nmpc):
+    from mpc_code_b200.mpc_loop import CompiledProblem
+    return CompiledProblem(nmpc.prob, "nmpc_cstr")
+
+
+def _handle(cp, B, **kw):
+    from mpc_code_b200.solvers import MpcbHandle, BatchedNlpSolver
+    h = MpcbHandle(cp.library, B, dict(max_iter=100), dict(max_iter=100, **kw))
+    return h, BatchedNlpSolver("ocp", cp.ocp_spec).attach(h), BatchedNlpSolver("target", cp.ss_spec).attach(h)
+
+
+def _unpack(Hp, nz):
+    H = np.zeros((nz, nz))
+    for i in range(nz):
+        for j in range(i + 1):
+            H[i, j] = H[j, i] = Hp[i * (i + 1) // 2 + j]
+    return H
+
+
+def test_stage_derivative_kernel_matches_symbolic_ad(nmpc, cp):
+    p, mod = nmpc.prob, nmpc.oracle
+    n, m, N = p.nx, p.nu, p.N
+    nz = n + m
+    rng = np.random.default_rng(0)
+    B = 64
+    par = np.stack([nmpc.ocp_par(p.x0_m * (1 + 0.01 * rng.standard_normal(3)), p.x0_m, p.u0, np.array([0.1 * rng.standard_normal(), 0.1 + 0.02 * rng.standard_normal()])) for _ in range(B)])
+    w = np.zeros((B, p.nw))
+    for k in range(N + 1):
+        w[:, nz * k:nz * k + n] = p.x0_m * (1 + 0.02 * rng.uniform(-1, 1, (B, n)))
+    for k in range(N):
+        w[:, nz * k + n:nz * (k + 1)] = p.u0 * (1 + 0.01 * rng.uniform(-1, 1, (B, m)))
+    lam = rng.standard_normal((B, N * n))
+    h, _, _ = _handle(cp, B)
+    A, Bm, c, Hh = [t.cpu().numpy() for t in h.stage_derivs(par, w, lam)]
+    for b in (0, 17, 63):
+        for k in (0, 13, 49):
+            X, U = w[b, nz * k:nz * k + n], w[b, nz * k + n:nz * (k + 1)]
+            F, J, Ho = mod.orc_dyn_d(X, U, par[b], np.zeros(p.npx), lam[b, k * n:(k + 1) * n])
+            assert np.allclose(A[b, k].reshape(n, n, order="F"), J[:, :n], rtol=1e-11, atol=1e-13)
+            assert np.allclose(Bm[b, k].reshape(n, m, order="F"), J[:, n:], rtol=1e-11, atol=1e-13)
+            assert np.allclose(_unpack(Hh[b, k], nz), Ho, rtol=1e-10, atol=1e-11 * np.abs(Ho).max())
+            assert np.allclose(c[b, k], F.ravel() - w[b, nz * (k + 1):nz * (k + 1) + n], rtol=0, atol=1e-11)
+
+
+def test_ocp_solutions_match_oracle_fixtures(nmpc, cp):
+    B = G["ocp_par"].shape[0]
+    h, solver, _ = _handle(cp, B)
+    sol = solver(lbx=nmpc.ocp.w_lb, ubx=nmpc.ocp.w_ub, x0=np.tile(G["ocp_w0"], (B, 1)), p=G["ocp_par"], lbg=nmpc.ocp.g_lb, ubg=nmpc.ocp.g_ub)
+    w, f = sol["x"].cpu().numpy(), sol["f"].cpu().numpy()
+    stats = solver.stats()
+    assert np.array_equal(stats["status"].cpu().numpy(), G["ocp_status"])
+    assert stats["return_status"][0] == "Solve_Succeeded"
+    assert np.array_equal(stats["iter_count"].cpu().numpy(), G["ocp_iters"])
+    assert np.abs(w - G["ocp_w"]).max() < U_TOL and np.abs(w - G["ocp_w"]).max() < 1e-8
+    assert np.all(np.abs(f - G["ocp_f"]) <= F_RTOL * np.maximum(1.0, np.abs(G["ocp_f"])))
+    n = nmpc.prob.nx
+    lb, ub = nmpc.ocp.w_lb, nmpc.ocp.w_ub
+    act = lambda W: (np.abs(W - lb) < 1e-6) | (np.abs(W - ub) < 1e-6)  # noqa: E731
+    assert np.array_equal(act(w)[:, n:], act(G["ocp_w"])[:, n:])
+
+
+def test_target_solutions_match_oracle_fixtures(nmpc, cp):
+    B = G["ss_par"].shape[0]
+    h, _, solver_ss = _handle(cp, B)
+    sol = solver_ss(lbx=nmpc.ss.w_lb, ubx=nmpc.ss.w_ub, x0=G["ss_w0"], p=G["ss_par"], lbg=nmpc.ss.g_lb, ubg=nmpc.ss.g_ub)
+    assert np.array_equal(solver_ss.stats()["status"].cpu().numpy(), G["ss_status"])
+    assert np.abs(sol["x"].cpu().numpy() - G["ss_w"]).max() < 1e-9
+    assert np.abs(sol["f"].cpu().numpy() - G["ss_f"]).max() < 1e-12
+
+
+def test_ekf_matches_oracle_fixtures(nmpc, cp):
+    p = nmpc.prob
+    h, _, _ = _handle(cp, 1)
+    h.set_const("Q_kf", p.estimator["Q"]); h.set_const("R_kf", p.estimator["R"])
+    h.set_const("dmin", p.estimator["dmin"]); h.set_const("dmax", p.estimator["dmax"])
+    xi = np.concatenate([p.x0_m, p.dhat0])[None, :]; P = p.estimator["P0"].reshape(1, -1)
+    for k in range(3):
+        xi, P = h.estimate(1, G["ekf_y"][k][None, :], p.u0[None, :], np.array([[k * p.h]]), np.zeros((1, p.npx)), np.zeros((1, p.npy)), xi, P)
+        assert np.abs(xi.cpu().numpy()[0] - G["ekf_xi"][k]).max() < 1e-9
+        assert np.abs(P.cpu().numpy().reshape(p.nxi, p.nxi) - G["ekf_P"][k]).max() < 1e-8 * np.abs(G["ekf_P"][k]).max()
+
+
+def test_closed_loop_matches_oracle_fixture(nmpc, cp):
+    """Eight closed-loop steps (estimator -> target -> OCP -> plant) for three instances."""
+    Ns, B = G["cl_noise"].shape[0], G["cl_x0"].shape[0]
+    ctl = cp.controller(B)
+    ctl.reset(x0_p=G["cl_x0"], x0_m=G["cl_x0"])
+    rec = ctl.run(Ns, noise=G["cl_noise"])
+    assert np.array_equal(rec["STATUS_DYN"].cpu().numpy(), G["cl_STATUS_DYN"])
+    for key, tol in (("U", U_TOL), ("X_HAT", 1e-6), ("D_HAT", 1e-6), ("XS", 1e-6), ("US", 1e-6), ("Xp", 1e-6), ("Yp", 1e-6)):
+        diff = np.abs(rec[key].cpu().numpy() - G["cl_" + key]).max()
+        assert diff < tol, (key, diff)
+    fd = np.abs(rec["F_DYN"].cpu().numpy() - G["cl_F_DYN"])
+    assert np.all(fd <= F_RTOL * np.maximum(1.0, np.abs(G["cl_F_DYN"])))
+
+
+def test_infeasible_output_row_reports_status_2_and_loop_falls_back(nmpc, cp):
+    p = nmpc.prob
+    xhat = p.x0_m.copy(); xhat[2] = 0.4995
+    h, solver, _ = _handle(cp, 2)
+    par = np.stack([nmpc.ocp_par(xhat, p.x0_m, p.u0, p.dhat0), nmpc.ocp_par(p.x0_m, p.x0_m, p.u0, p.dhat0)])
+    solver(x0=np.tile(nmpc.cold_guess(), (2, 1)), p=par)
+    assert solver.stats()["return_status"] == ["Infeasible_Problem_Detected", "Solve_Succeeded"]
+
+
+def test_full_size_batch_properties(nmpc, cp):
+    """BASELINE config: 4 096 perturbed instances.  Size-independent properties instead of an oracle run:
+    permutation equivariance (instances are independent), dynamics feasibility of every solution, bounds."""
+    p = nmpc.prob
+    n, m, N = p.nx, p.nu, p.N
+    nz = n + m
+    B = 4096
+    rng = np.random.default_rng(20240419)
+    xh = p.x0_m * (1 + 0.02 * rng.uniform(-1, 1, (B, 3)))
+    xh[:, 2] = np.maximum(xh[:, 2], 0.51)
+    par = np.stack([nmpc.ocp_par(xh[i], p.x0_m, p.u0, p.dhat0) for i in range(B)])
+    h, solver, _ = _handle(cp, B)
+    w0 = np.tile(nmpc.cold_guess(), (B, 1))
+    w = solver(x0=w0, p=par)["x"]
+    st = solver.stats()["status"].cpu().numpy()
+    assert np.all(st == 0)
+    perm = rng.permutation(B)
+    w2 = solver(x0=w0, p=par[perm])["x"]
+    assert (w[perm] - w2).abs().max().item() == 0.0                       # bit-identical per instance
+    wn = w.cpu().numpy()
+    assert np.all(wn[:, n:] >= nmpc.ocp.w_lb[n:] - 1e-7) and np.all(wn[:, n:] <= nmpc.ocp.w_ub[n:] + 1e-7)
+    # defects of the returned trajectories, re-evaluated by the independent model-step entry point
+    x = wn[:, :nz * N].reshape(B, N, nz)
+    for k in (0, 1, 25, 49):
+        xn = h.model_step(x[:, k, :n], x[:, k, n:], np.tile(p.dhat0, (B, 1)), np.zeros((B, 1)), np.zeros((B, p.npx))).cpu().numpy()
+        nxt = wn[:, nz * (k + 1):nz * (k + 1) + n]
+        assert np.abs(xn - nxt).max() < 1e-7
+    # oracle spot-check of a few instances out of the big batch
+    from oracle.nlp import OcpNlp
+    from oracle.ipm import IpmOptions
+    on = OcpNlp(nmpc.ocp, nmpc.oracle)
+    for i in (0, 1234, 4095):
+        lb, ub = nmpc.ocp.w_lb.copy(), nmpc.ocp.w_ub.copy(); lb[:n] = ub[:n] = xh[i]
+        r = on.solve(w0[i], par[i], lb, ub, opts=IpmOptions(max_iter=100))
+        assert r.status == 0 and np.abs(r.x - wn[i]).max() < U_TOL
