@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""Benchmark of the batched MPC hot path (estimator -> target -> OCP -> input extraction).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # CPU arm: the oracle port on all host cores
+
+Workload at N=1 (BASELINE.json configs[1]): Ex_NMPC - nonlinear CSTR NMPC with EKF, horizon 50, Mx=10,
+batch 4 096 instances with perturbed initial states.  With N>1 every rank runs its
+own 4 096 instances (weak scaling, no data-path collective); NCCL only gathers the closed-loop inputs and
+solver statistics after the timed region.  One JSON line is printed by rank 0.
+"""
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH_PER_GPU = 4096
+SEED_X0, SEED_NOISE = 20240419, 7
+METRIC = "batched MPC steps/sec (Ex_NMPC CSTR, N=50, FP64)"
+
+
+def _problem():
+    import __graft_entry__ as entry
+    return entry._problem("nmpc_cstr")
+
+
+def _workload(prob, B, nsteps, rank=0):
+    rng = np.random.default_rng(SEED_X0 + 1000003 * rank)
+    x0 = prob.x0_p * (1 + 0.02 * rng.uniform(-1, 1, (B, prob.nxp)))
+    noise = np.sqrt(1e-7) * np.random.default_rng(SEED_NOISE + rank).standard_normal((nsteps, B, prob.ny))
+    return x0, noise
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm (the oracle port): used for `cpu_baseline` and for `--impl reference`
+# ---------------------------------------------------------------------------------------------
+_ORACLE = {}
+
+
+def _oracle_init():
+    for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[var] = "1"                         # one core per worker process
+    sys.path.insert(0, ROOT)
+    from oracle import cmodel
+    from oracle.closed_loop import OracleLoop
+    prob, ss, ocp = _problem()
+    _ORACLE["loop"] = OracleLoop(prob, ss, ocp, cmodel.build("nmpc_cstr", prob, ocp, ss))
+
+
+def _oracle_worker(args):
+    x0, noise, nsteps = args
+    t0 = time.time()
+    rec = _ORACLE["loop"].run(Nsim=nsteps, x0_p=x0, x0_m=x0, noise=noise)
+    return time.time() - t0, int(np.sum(rec["ITER_DYN"]))
+
+
+class OraclePool:
+    """Worker processes (spawned, so no BLAS thread state is inherited), each holding the CPU oracle."""
+
+    def __init__(self, cores):
+        self.cores = cores
+        self.pool = mp.get_context("spawn").Pool(cores, initializer=_oracle_init)
+        prob, _, _ = _problem()
+        x0, noise = _workload(prob, cores, 1)
+        self.pool.map(_oracle_worker, [(x0[i], noise[:, i, :], 1) for i in range(cores)], chunksize=1)   # warm up
+        self.prob = prob
+
+    def throughput(self, n_inst, nsteps):
+        """Closed-loop instance-steps per second over all workers."""
+        x0, noise = _workload(self.prob, n_inst, nsteps)
+        jobs = [(x0[i], noise[:, i, :], nsteps) for i in range(n_inst)]
+        t0 = time.time()
+        self.pool.map(_oracle_worker, jobs, chunksize=1)
+        wall = time.time() - t0
+        return n_inst * nsteps / wall, wall
+
+    def close(self):
+        self.pool.close(); self.pool.join()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_inst = cores                                   # one instance per core per step
+    pool = OraclePool(cores)
+    samples = []
+    for _ in range(args.warmup):
+        pool.throughput(n_inst, 1)
+    t0 = time.time()
+    for _ in range(args.steps):
+        v, _ = pool.throughput(n_inst, 1)
+        samples.append(v)
+    wall = time.time() - t0
+    pool.close()
+    value = float(np.mean(samples))
+    sample = "%d instances x 1 closed-loop step per bench step, one process per core" % n_inst
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "Ex_NMPC CSTR NMPC+EKF, N=50, Mx=10; CPU oracle port (dense IPM, not IPOPT)", "batch": n_inst},
+        "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def _clock_sampler(path):
+    q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    try:
+        return subprocess.Popen(["nvidia-smi", "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                stdout=open(path, "w"), stderr=subprocess.DEVNULL)
+    except Exception:
+        return None
+
+
+def _parse_clocks(path, gpu_index):
+    sm, smax, reasons = [], 0.0, set()
+    try:
+        for line in open(path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9 or not f[0].isdigit() or int(f[0]) != gpu_index:
+                continue
+            sm.append(float(f[1])); smax = max(smax, float(f[2]))
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+    except Exception:
+        pass
+    return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax or None, "reasons": sorted(reasons),
+            "samples": len(sm)}
+
+
+def stage_flops(cp):
+    """Algorithmic FLOPs of one stage's derivative evaluation (DAG op counts; see DESIGN.md 'FLOP accounting')."""
+    p, f = cp.prob, cp.flops
+    nx, nz = p.nx, p.nx + p.nu
+    nzp = nz * (nz + 1) // 2
+    mx = cp.library.dims.Mx
+    per_sub = 4 * (f["mdl_f"] + f["mdl_f_vjp"] + f["mdl_f_sh"]) + 13 * nx + 15 * nx + 13 * nx * (nz + 1) + 4 * nzp
+    return mx * per_sub + f.get("mdl_post", 0) + f["ocp_cost_d"] + f.get("ocp_out_d", 0) + 2 * nx
+
+
+def stage_bytes(cp):
+    """Algorithmic HBM bytes of one stage's derivative evaluation: x,u,x+,lam,ym,s in; A,B,c,H,grad,G,g,partials out."""
+    p = cp.prob
+    nx, nu, ng = p.nx, p.nu, cp.library.dims.ng
+    nz = nx + nu
+    rd = nz + nx + nx + 2 * ng + (p.nd + 1 + p.npx + p.npy + 2 * nz)
+    wr = nx * nx + nx * nu + nx + nz * (nz + 1) // 2 + nz + ng * nz + ng + 2
+    return 8 * (rd + wr)
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from mpc_code_b200.mpc_loop import CompiledProblem
+    prob, ss, ocp = _problem()
+    cp = CompiledProblem(prob, "nmpc_cstr")
+    B, K, W = BATCH_PER_GPU, args.steps, args.warmup
+    total = W + K
+    x0, noise = _workload(prob, B, total, rank)
+    ctl = cp.controller(B)
+    noise_dev = torch.as_tensor(noise, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---------------- device-resident closed loop (value) ----------------
+    ctl.reset(x0_p=x0, x0_m=x0)
+    ys, us, stat = [], [], []
+    for k in range(W):
+        o = ctl.step(noise_dev[k]); ys.append(o["Yp"]); us.append(o["U"])
+    clock_file = os.path.join(tempfile.gettempdir(), "mpcb_clocks_%d.csv" % os.getpid())
+    sampler = _clock_sampler(clock_file) if rank == 0 else None
+    ctl.h.set_profiling(True)
+    launches0 = ctl.h.launches
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+    barrier()
+    ev[0].record()
+    for k in range(K):
+        o = ctl.step(noise_dev[W + k])
+        ev[k + 1].record()
+        ys.append(o["Yp"]); us.append(o["U"]); stat.append((o["STATUS_DYN"], o["ITER_DYN"], o["STATUS_SS"]))
+    barrier()
+    elapsed_ms = ev[0].elapsed_time(ev[K])
+    prof = ctl.h.profile()
+    ctl.h.set_profiling(False)
+    launches = ctl.h.launches - launches0
+    step_ms = np.array([ev[k].elapsed_time(ev[k + 1]) for k in range(K)])
+    if sampler is not None:
+        sampler.terminate(); sampler.wait()
+    t_all = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
+    elapsed_max = float(t_all.item())
+    value = world * B * K / (elapsed_max * 1e-3)
+
+    # ---------------- end to end through the public API with host buffers (e2e) ----------------
+    y_host = torch.stack(ys).cpu().pin_memory()                      # recorded plant measurements, [W+K, B, ny]
+    u_host = torch.empty(total, B, prob.nu, dtype=torch.float64).pin_memory()
+    y_dev = torch.empty(B, prob.ny, device=dev, dtype=torch.float64)
+    ctl.reset(x0_p=x0, x0_m=x0)
+    for k in range(W):
+        y_dev.copy_(y_host[k], non_blocking=True); o = ctl.step(y_meas=y_dev); u_host[k].copy_(o["U"], non_blocking=True)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(W, total):
+        y_dev.copy_(y_host[k], non_blocking=True)                    # H2D of this step's measurement
+        o = ctl.step(y_meas=y_dev)
+        u_host[k].copy_(o["U"], non_blocking=True)                   # D2H of the computed inputs
+        torch.cuda.current_stream(dev).synchronize()                 # the caller needs u_k before the next sample
+    e1.record()
+    barrier()
+    t_e2e = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * K / (float(t_e2e.item()) * 1e-3)
+    replay_err = float((u_host[W:].to(dev) - torch.stack(us[W:])).abs().max().item())
+
+    # ---------------- statistics gathered over NCCL (the only collective; off the timed path) ----------------
+    st_dyn = torch.stack([s[0] for s in stat]); it_dyn = torch.stack([s[1] for s in stat]).double()
+    counts = torch.tensor([(st_dyn == 0).sum(), (st_dyn == 1).sum(), (st_dyn == 2).sum(), (st_dyn < 0).sum(),
+                           it_dyn.sum(), float(st_dyn.numel())], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(counts)
+        gathered = [torch.empty_like(us[-1]) for _ in range(world)]
+        dist.all_gather(gathered, us[-1].contiguous())               # closed-loop inputs of the last step, all ranks
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- roofline of the dominant kernel (stage derivatives, class ocp_eval) ----------------
+    kms = prof["ms"]; kl = prof["launches"]
+    dom = max(("ocp_eval", "ocp_kkt", "ocp_trial", "target", "estimate"), key=lambda c: kms[c])
+    f_stage, b_stage = stage_flops(cp), stage_bytes(cp)
+    eval_s = kms["ocp_eval"] * 1e-3
+    evals = prof["eval_instances"] * prob.N                           # stage evaluations done in the timed region
+    fp64_peak = ctl.h.dfma_peak_tflops()
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak, hbm_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback")
+    ach_tf = evals * f_stage / eval_s / 1e12 if eval_s > 0 else 0.0
+    ach_gb = evals * b_stage / eval_s / 1e9 if eval_s > 0 else 0.0
+    roofline = {
+        "kernel": "k_ocp_eval", "bound": "fp64", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+        "frac": ach_tf / fp64_peak if fp64_peak else None, "traffic": None,
+        "peak_source": "FP64 FMA micro-benchmark run in this process (mpcb_dfma_peak); MEASURED_PEAKS.json has no FP64 entry",
+        "flops_per_stage_eval": f_stage, "stage_evals": int(evals), "kernel_ms_total": kms["ocp_eval"],
+        "kernel_launches": kl["ocp_eval"], "avg_launch_ms": kms["ocp_eval"] / max(kl["ocp_eval"], 1),
+        "hbm": {"achieved": ach_gb, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gb / hbm_peak, "bytes_per_stage_eval": b_stage,
+                "peak_source": hbm_src},
+        "kernel_time_share": {c: kms[c] / max(sum(kms.values()), 1e-12) for c in kms}, "dominant_by_time": dom,
+    }
+
+    # ---------------- CPU baseline beside it (bounded sample) ----------------
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        pool = OraclePool(cores)
+        v, wall = pool.throughput(cores, 2)
+        pool.close()
+        cpu_baseline = {"value": v, "unit": "steps/s", "cores": cores, "kind": "port",
+                        "sample": "%d instances x 2 closed-loop steps of the same workload, one process per core (%.1f s); "
+                                  "dense-KKT oracle port, not IPOPT" % (cores, wall)}
+    clocks = _parse_clocks(clock_file, local)
+    n_inst = counts[5].item()
+    out = {
+        "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": elapsed_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "Ex_NMPC (configs[1]): CSTR NMPC + EKF + target, N=50, Mx=10, closed loop with plant and "
+                               "measurement noise; %d instances per GPU, x0 perturbed 2%% (seed %d)" % (B, SEED_X0),
+                   "batch_per_gpu": B, "global_batch": world * B, "parallelism": "instances sharded, %d rank(s)" % world,
+                   "cache": "per-step working set %.0f MB per GPU > 126 MB L2 (no flush needed)" % (B * cp_ws_bytes(cp) / 1e6)},
+        "p50_step_latency_ms": float(np.median(step_ms)), "p99_step_latency_ms": float(np.percentile(step_ms, 99)),
+        "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": B * prob.ny * 8, "d2h_bytes_per_step": B * prob.nu * 8,
+                "replay_max_abs_du": replay_err},
+        "gpu_launches": int(launches),
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
+        "solver_stats": {"solve_succeeded": counts[0].item() / n_inst, "acceptable": counts[1].item() / n_inst,
+                         "infeasible": counts[2].item() / n_inst, "failed": counts[3].item() / n_inst,
+                         "mean_ipm_iterations": counts[4].item() / n_inst},
+    }
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cp_ws_bytes(cp):
+    d = cp.library.dims
+    nz = d.nx + d.nu
+    per_stage = d.nx * d.nx * 2 + d.nx * d.nu * 2 + nz * (nz + 1) // 2 + 2 * nz + 6 * d.nx + d.ng * (nz + 8) + 8
+    return 8 * (d.N * per_stage + 4 * d.nw + d.npar)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -116,6 +116,20 @@ int  mpcb_model_step(mpcb_handle_t h, const double* x, const double* u, const do
 int  mpcb_stage_derivs(mpcb_handle_t h, const double* par, const double* w, const double* lam,
                        double* A, double* Bm, double* c, double* H, void* stream);
 
+/* Profiling.  With profiling on, every kernel launch is bracketed by CUDA events on its stream and the
+ * time is accumulated per kernel class: 0 ocp_init, 1 ocp_eval (stage derivatives), 2 ocp_kkt (Riccati
+ * step), 3 ocp_trial (line-search evaluation), 4 ocp_accept, 5 target, 6 estimate, 7 other.
+ * instance_counts[0] = number of (instance) derivative evaluations done by class 1,
+ * instance_counts[1] = number of (instance) trial evaluations done by class 3.
+ * mpcb_set_profiling resets the accumulators.  Launch counts are kept even with profiling off. */
+int  mpcb_set_profiling(mpcb_handle_t h, int on);
+int  mpcb_get_profile(mpcb_handle_t h, double* kernel_ms /*[8]*/, long* kernel_launches /*[8]*/,
+                      unsigned long long* instance_counts /*[2]*/);
+
+/* FP64 FMA issue-rate micro-benchmark of the current device (8 independent chains per thread):
+ * the measured denominator for FP64 roofline fractions (MEASURED_PEAKS.json has no FP64 entry). */
+int  mpcb_dfma_peak(int iters, double* tflops);
+
 /* Counters of the last mpcb_ocp / mpcb_target call: kernel launches, solver ticks. */
 int  mpcb_last_launches(mpcb_handle_t h);
 int  mpcb_last_ticks(mpcb_handle_t h);

@@ -6,8 +6,13 @@
 #include <stdio.h>
 #include <string.h>
 #include <string>
+#include <utility>
+#include <vector>
 #include "mpcb.h"
 #include "mpcb_target.cuh"
+
+#define MPCB_NKERNELS 8
+enum { KC_OCP_INIT = 0, KC_OCP_EVAL = 1, KC_OCP_KKT = 2, KC_OCP_TRIAL = 3, KC_OCP_ACCEPT = 4, KC_TARGET = 5, KC_ESTIMATE = 6, KC_OTHER = 7 };
 
 #ifndef MPCB_FLOPS_TABLE
 #define MPCB_FLOPS_TABLE
@@ -20,6 +25,7 @@
 struct OcpArgs {
     int B;
     const double* par; double* w; double* ws; InstState* st;
+    unsigned long long* counters;      // [0] instance-evaluations (derivatives), [1] instance-trials (line search)
     OcpShared S;
 };
 
@@ -40,6 +46,7 @@ __global__ void __launch_bounds__(128) k_ocp_eval(OcpArgs a) {
     const int inst = tid / NH, k = tid % NH;
     if (inst >= a.B) return;
     if (a.st[inst].state != ST_EVAL) return;
+    if (k == 0) atomicAdd(a.counters, 1ULL);
     OcpInst I = ocp_view(a, inst);
     ocp_eval_stage(I, a.S, k);
 }
@@ -57,6 +64,7 @@ __global__ void __launch_bounds__(128) k_ocp_trial(OcpArgs a) {
     const int inst = tid / NH, k = tid % NH;
     if (inst >= a.B) return;
     if (a.st[inst].state != ST_LS) return;
+    if (k == 0) atomicAdd(a.counters + 1, 1ULL);
     OcpInst I = ocp_view(a, inst);
     ocp_trial_stage(I, a.S, k);
 }
@@ -171,6 +179,13 @@ struct mpcb_ctx {
     InstState* st;
     int* n_active; int* h_active;
     int have_dbounds, last_launches, last_ticks;
+    // profiling (mpcb_set_profiling): CUDA-event time and launch count per kernel class
+    int profile;
+    unsigned long long* counters;
+    double kernel_ms[MPCB_NKERNELS]; long kernel_launches[MPCB_NKERNELS];
+    unsigned long long eval_instances, trial_instances;
+    std::vector<cudaEvent_t> ev_pool;
+    std::vector<std::pair<int, int>> ev_pending;   // (kernel class, index of start event; stop = +1)
 };
 
 static IpmOpts to_ipm(const mpcb_opts_t& o) {
@@ -186,6 +201,41 @@ static int fail(mpcb_ctx* h, const char* what, cudaError_t e) {
     return -1;
 }
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(h, #call, e_); } while (0)
+
+// Launch bracket: with profiling on, a pair of events goes around the launch on its own stream.
+struct Prof {
+    mpcb_ctx* h; cudaStream_t s; int kc; int idx;
+    Prof(mpcb_ctx* h_, cudaStream_t s_, int kc_) : h(h_), s(s_), kc(kc_), idx(-1) {
+        if (!h->profile) return;
+        idx = (int)h->ev_pending.size() * 2;
+        while ((int)h->ev_pool.size() < idx + 2) { cudaEvent_t e; cudaEventCreate(&e); h->ev_pool.push_back(e); }
+        cudaEventRecord(h->ev_pool[idx], s);
+    }
+    ~Prof() {
+        h->kernel_launches[kc] += 1;
+        if (idx < 0) return;
+        cudaEventRecord(h->ev_pool[idx + 1], s);
+        h->ev_pending.push_back(std::make_pair(kc, idx));
+    }
+};
+static void prof_collect(mpcb_ctx* h) {       // call after the stream has been synchronised
+    for (auto& p : h->ev_pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, h->ev_pool[p.second], h->ev_pool[p.second + 1]) == cudaSuccess) h->kernel_ms[p.first] += ms;
+    }
+    h->ev_pending.clear();
+}
+
+__global__ void k_dfma_peak(double* out, int iters) {
+    // 8 independent FMA chains per thread: measures the FP64 FMA issue rate of the part
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double b = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+        a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
 
 extern "C" {
 
@@ -243,6 +293,10 @@ int mpcb_create(int batch, const mpcb_opts_t* oss, const mpcb_opts_t* odyn, mpcb
     CK(cudaMemset(h->Kest, 0, sizeof(double) * NXI * NY));
     CK(cudaMalloc(&h->n_active, sizeof(int)));
     CK(cudaMallocHost(&h->h_active, sizeof(int)));
+    CK(cudaMalloc(&h->counters, 2 * sizeof(unsigned long long)));
+    CK(cudaMemset(h->counters, 0, 2 * sizeof(unsigned long long)));
+    h->profile = 0; h->eval_instances = h->trial_instances = 0;
+    for (int i = 0; i < MPCB_NKERNELS; ++i) { h->kernel_ms[i] = 0.0; h->kernel_launches[i] = 0; }
     return 0;
 }
 
@@ -250,7 +304,8 @@ int mpcb_destroy(mpcb_handle_t h) {
     if (!h) return 0;
     cudaFree(h->ws); cudaFree(h->st); cudaFree(h->lbx); cudaFree(h->ubx); cudaFree(h->lbg); cudaFree(h->ubg);
     cudaFree(h->ss_lbx); cudaFree(h->ss_ubx); cudaFree(h->Qkf); cudaFree(h->Rkf); cudaFree(h->Kest);
-    cudaFree(h->dmin); cudaFree(h->dmax); cudaFree(h->n_active); cudaFreeHost(h->h_active);
+    cudaFree(h->dmin); cudaFree(h->dmax); cudaFree(h->n_active); cudaFreeHost(h->h_active); cudaFree(h->counters);
+    for (auto e : h->ev_pool) cudaEventDestroy(e);
     delete h;
     return 0;
 }
@@ -285,30 +340,38 @@ int mpcb_ocp(mpcb_handle_t h, const double* par, double* w, double* f, int* stat
 #if MPCB_HAS_OCP
     cudaStream_t s = (cudaStream_t)stream;
     OcpArgs a;
-    a.B = h->B; a.par = par; a.w = w; a.ws = h->ws; a.st = h->st;
+    a.B = h->B; a.par = par; a.w = w; a.ws = h->ws; a.st = h->st; a.counters = h->counters;
     a.S.lbx = h->lbx; a.S.ubx = h->ubx; a.S.lbg = h->lbg; a.S.ubg = h->ubg; a.S.o = to_ipm(h->opts_dyn);
     const int bs = 128;
     const long nst = (long)h->B * NH;
     int launches = 0, ticks = 0;
-    k_ocp_init<<<nblk((long)h->B * (NH + 1), bs), bs, 0, s>>>(a); launches++;
+    { Prof p(h, s, KC_OCP_INIT); k_ocp_init<<<nblk((long)h->B * (NH + 1), bs), bs, 0, s>>>(a); } launches++;
     // every instance needs at most max_iter+1 evaluations plus its line-search backtracks
     const int max_ticks = (h->opts_dyn.max_iter + 2) * 8;
     const int check_every = 2;
     while (ticks < max_ticks) {
         for (int c = 0; c < check_every; ++c) {
-            k_ocp_eval<<<nblk(nst, bs), bs, 0, s>>>(a);
-            k_ocp_kkt<<<nblk(h->B, 64), 64, 0, s>>>(a);
-            k_ocp_trial<<<nblk(nst, bs), bs, 0, s>>>(a);
+            { Prof p(h, s, KC_OCP_EVAL); k_ocp_eval<<<nblk(nst, bs), bs, 0, s>>>(a); }
+            { Prof p(h, s, KC_OCP_KKT); k_ocp_kkt<<<nblk(h->B, 64), 64, 0, s>>>(a); }
+            { Prof p(h, s, KC_OCP_TRIAL); k_ocp_trial<<<nblk(nst, bs), bs, 0, s>>>(a); }
             if (c == check_every - 1) CK(cudaMemsetAsync(h->n_active, 0, sizeof(int), s));
-            k_ocp_accept<<<nblk(h->B, 64), 64, 0, s>>>(a, h->n_active);
+            { Prof p(h, s, KC_OCP_ACCEPT); k_ocp_accept<<<nblk(h->B, 64), 64, 0, s>>>(a, h->n_active); }
             launches += 4; ticks++;
         }
         CK(cudaMemcpyAsync(h->h_active, h->n_active, sizeof(int), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
+        prof_collect(h);
         if (*h->h_active == 0) break;
     }
-    k_ocp_output<<<nblk(h->B, 128), 128, 0, s>>>(a, f, status, iters); launches++;
+    { Prof p(h, s, KC_OTHER); k_ocp_output<<<nblk(h->B, 128), 128, 0, s>>>(a, f, status, iters); } launches++;
     CK(cudaGetLastError());
+    if (h->profile) {
+        unsigned long long cnt[2];
+        CK(cudaMemcpyAsync(cnt, h->counters, sizeof(cnt), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        prof_collect(h);
+        h->eval_instances = cnt[0]; h->trial_instances = cnt[1];
+    }
     h->last_launches = launches; h->last_ticks = ticks;
     return 0;
 #else
@@ -319,7 +382,7 @@ int mpcb_ocp(mpcb_handle_t h, const double* par, double* w, double* f, int* stat
 int mpcb_stage_derivs(mpcb_handle_t h, const double* par, const double* w, const double* lam,
                       double* A, double* Bm, double* c, double* H, void* stream) {
 #if MPCB_HAS_OCP
-    k_stage_derivs<<<nblk((long)h->B * NH, 128), 128, 0, (cudaStream_t)stream>>>(h->B, par, w, lam, A, Bm, c, H);
+    { Prof p(h, (cudaStream_t)stream, KC_OTHER); k_stage_derivs<<<nblk((long)h->B * NH, 128), 128, 0, (cudaStream_t)stream>>>(h->B, par, w, lam, A, Bm, c, H); }
     CK(cudaGetLastError());
     h->last_launches = 1;
     return 0;
@@ -331,9 +394,10 @@ int mpcb_stage_derivs(mpcb_handle_t h, const double* par, const double* w, const
 int mpcb_target(mpcb_handle_t h, const double* par_ss, double* wss, double* fss, int* status, int* iters, void* stream) {
 #if MPCB_HAS_TARGET
     TgtShared S; S.lbx = h->ss_lbx; S.ubx = h->ss_ubx; S.o = to_ipm(h->opts_ss);
-    k_target<<<nblk(h->B, 64), 64, 0, (cudaStream_t)stream>>>(h->B, par_ss, wss, fss, status, iters, S);
+    { Prof p(h, (cudaStream_t)stream, KC_TARGET); k_target<<<nblk(h->B, 64), 64, 0, (cudaStream_t)stream>>>(h->B, par_ss, wss, fss, status, iters, S); }
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize((cudaStream_t)stream));
+    prof_collect(h);
     h->last_launches = 1; h->last_ticks = 1;
     return 0;
 #else
@@ -344,13 +408,14 @@ int mpcb_target(mpcb_handle_t h, const double* par_ss, double* wss, double* fss,
 int mpcb_estimate(mpcb_handle_t h, int est_type, const double* y, const double* u, const double* t, const double* px,
                   const double* py, double* xi, double* P, void* stream) {
     EstShared E; E.Q = h->Qkf; E.R = h->Rkf; E.K = h->Kest; E.dmin = h->dmin; E.dmax = h->dmax; E.has_dbounds = h->have_dbounds;
-    k_estimate<<<nblk(h->B, 64), 64, 0, (cudaStream_t)stream>>>(h->B, est_type, y, u, t, px, py, xi, P, E);
+    { Prof p(h, (cudaStream_t)stream, KC_ESTIMATE); k_estimate<<<nblk(h->B, 64), 64, 0, (cudaStream_t)stream>>>(h->B, est_type, y, u, t, px, py, xi, P, E); }
     CK(cudaGetLastError());
     return 0;
 }
 
 int mpcb_model_output(mpcb_handle_t h, const double* x, const double* u, const double* d, const double* t,
                       const double* py, double* y, void* stream) {
+    h->kernel_launches[KC_OTHER] += 1;
     k_model_output<<<nblk(h->B, 128), 128, 0, (cudaStream_t)stream>>>(h->B, x, u, d, t, py, y);
     CK(cudaGetLastError());
     return 0;
@@ -358,6 +423,7 @@ int mpcb_model_output(mpcb_handle_t h, const double* x, const double* u, const d
 
 int mpcb_model_step(mpcb_handle_t h, const double* x, const double* u, const double* d, const double* t,
                     const double* px, double* xn, void* stream) {
+    h->kernel_launches[KC_OTHER] += 1;
     k_model_step<<<nblk(h->B, 128), 128, 0, (cudaStream_t)stream>>>(h->B, x, u, d, t, px, xn);
     CK(cudaGetLastError());
     return 0;
@@ -366,6 +432,7 @@ int mpcb_model_step(mpcb_handle_t h, const double* x, const double* u, const dou
 int mpcb_plant_meas(mpcb_handle_t h, const double* x, const double* u, const double* t, const double* pyp,
                     const double* pymp, const double* noise, double* y, void* stream) {
 #if !MPCB_PLANT_NOMINAL
+    h->kernel_launches[KC_OTHER] += 1;
     k_plant_meas<<<nblk(h->B, 128), 128, 0, (cudaStream_t)stream>>>(h->B, x, u, t, pyp, pymp, noise, y);
     CK(cudaGetLastError());
     return 0;
@@ -377,12 +444,48 @@ int mpcb_plant_meas(mpcb_handle_t h, const double* x, const double* u, const dou
 int mpcb_plant_step(mpcb_handle_t h, double* x, const double* u, const double* t, const double* pxp,
                     const double* pxmp, void* stream) {
 #if !MPCB_PLANT_NOMINAL
+    h->kernel_launches[KC_OTHER] += 1;
     k_plant_step<<<nblk(h->B, 128), 128, 0, (cudaStream_t)stream>>>(h->B, x, u, t, pxp, pxmp);
     CK(cudaGetLastError());
     return 0;
 #else
     h->err = "nominal plant: use mpcb_model_step (MPC_code.py:813-814)"; return -3;
 #endif
+}
+
+int mpcb_set_profiling(mpcb_handle_t h, int on) {
+    h->profile = on ? 1 : 0;
+    for (int i = 0; i < MPCB_NKERNELS; ++i) { h->kernel_ms[i] = 0.0; h->kernel_launches[i] = 0; }
+    h->eval_instances = h->trial_instances = 0;
+    cudaMemset(h->counters, 0, 2 * sizeof(unsigned long long));
+    return 0;
+}
+
+int mpcb_get_profile(mpcb_handle_t h, double* kernel_ms, long* kernel_launches, unsigned long long* instance_counts) {
+    for (int i = 0; i < MPCB_NKERNELS; ++i) { kernel_ms[i] = h->kernel_ms[i]; kernel_launches[i] = h->kernel_launches[i]; }
+    instance_counts[0] = h->eval_instances; instance_counts[1] = h->trial_instances;
+    return 0;
+}
+
+int mpcb_dfma_peak(int iters, double* tflops) {
+    const int blocks = 148 * 16, threads = 256;
+    double* out = nullptr;
+    if (cudaMalloc(&out, sizeof(double) * blocks * threads) != cudaSuccess) return -1;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    k_dfma_peak<<<blocks, threads>>>(out, 1000);
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0);
+        k_dfma_peak<<<blocks, threads>>>(out, iters);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(out); return -1; }
+        float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
+        const double fl = 2.0 * 8.0 * (double)iters * blocks * threads;
+        if (ms > 0.f && fl / (ms * 1e-3) / 1e12 > best) best = fl / (ms * 1e-3) / 1e12;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+    *tflops = best;
+    return 0;
 }
 
 int mpcb_last_launches(mpcb_handle_t h) { return h->last_launches; }

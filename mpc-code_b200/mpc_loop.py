@@ -115,7 +115,9 @@ class BatchedMpc:
         return p_xk, p_yk, p_xmp, p_ymp, p_xp, p_yp
 
     # -- one closed-loop step -----------------------------------------------------
-    def step(self, noise=None, state_noise=None, time_phases: bool = False) -> Dict[str, object]:
+    def step(self, noise=None, state_noise=None, time_phases: bool = False, y_meas=None) -> Dict[str, object]:
+        """One closed-loop step.  With ``y_meas`` (``[B, ny]``) the measurement comes from the caller (a real
+        plant) and the built-in plant simulation (``MPC_code.py:531-541,813-827``) is skipped."""
         p, t, h = self.prob, self.torch, self.h
         nx, nu, ny, nd, N, B = p.nx, p.nu, p.ny, p.nd, p.N, self.B
         nxu = nx + nu
@@ -130,7 +132,9 @@ class BatchedMpc:
         offree = p.flags["offree"]
         # model and plant outputs (:524-541)
         yhat_k = h.model_output(self.xhat_k, self.u_k, self.dhat_k, tt, p_y_k)
-        if nominal:
+        if y_meas is not None:
+            y_k = h.tensor(y_meas, ny)
+        elif nominal:
             y_k = h.model_output(self.x_k, self.u_k, self.dhat_k, tt, p_y_k)
             if noise is not None:
                 y_k = y_k + h.tensor(noise, ny)
@@ -195,6 +199,9 @@ class BatchedMpc:
             out["U"] = self.u_k.clone()
             out["STATUS_DYN"], out["ITER_DYN"], out["F_DYN"] = st, self.solver.stats()["iter_count"], sol["f"]
         # plant step (:813-827)
+        if y_meas is not None:
+            self.ksim += 1
+            return out
         if nominal:
             self.x_k = h.model_step(self.x_k, self.u_k, self.dhat_k, tt, row(p_xmp))
         else:

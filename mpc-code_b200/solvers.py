@@ -34,7 +34,7 @@ class MpcbOpts(ctypes.Structure):
 C_SYMBOLS = ("mpcb_abi_version", "mpcb_default_opts", "mpcb_get_dims", "mpcb_model_flops", "mpcb_create",
              "mpcb_destroy", "mpcb_last_error", "mpcb_set_const", "mpcb_estimate", "mpcb_target", "mpcb_ocp",
              "mpcb_plant_meas", "mpcb_plant_step", "mpcb_model_output", "mpcb_model_step", "mpcb_stage_derivs",
-             "mpcb_last_launches", "mpcb_last_ticks")
+             "mpcb_last_launches", "mpcb_last_ticks", "mpcb_set_profiling", "mpcb_get_profile", "mpcb_dfma_peak")
 
 
 class MpcbLibrary:
@@ -64,6 +64,10 @@ class MpcbLibrary:
         L.mpcb_model_step.argtypes = [vp] * 8
         L.mpcb_stage_derivs.argtypes = [vp] * 9
         L.mpcb_last_launches.argtypes = [vp]; L.mpcb_last_ticks.argtypes = [vp]
+        L.mpcb_set_profiling.argtypes = [vp, ci]
+        L.mpcb_get_profile.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_long),
+                                       ctypes.POINTER(ctypes.c_ulonglong)]
+        L.mpcb_dfma_peak.argtypes = [ci, ctypes.POINTER(ctypes.c_double)]
         self.dims = MpcbDims()
         L.mpcb_get_dims(ctypes.byref(self.dims))
 
@@ -226,6 +230,26 @@ class MpcbHandle:
     @property
     def last_ticks(self):
         return self.L.mpcb_last_ticks(self._h)
+
+    KERNEL_CLASSES = ("ocp_init", "ocp_eval", "ocp_kkt", "ocp_trial", "ocp_accept", "target", "estimate", "other")
+
+    def set_profiling(self, on: bool):
+        self._check(self.L.mpcb_set_profiling(self._h, 1 if on else 0))
+
+    def profile(self):
+        """Accumulated CUDA-event time [ms] and launch count per kernel class since `set_profiling`."""
+        ms = (ctypes.c_double * 8)(); ln = (ctypes.c_long * 8)(); cnt = (ctypes.c_ulonglong * 2)()
+        self._check(self.L.mpcb_get_profile(self._h, ms, ln, cnt))
+        return dict(ms=dict(zip(self.KERNEL_CLASSES, list(ms))), launches=dict(zip(self.KERNEL_CLASSES, list(ln))),
+                    eval_instances=int(cnt[0]), trial_instances=int(cnt[1]))
+
+    def dfma_peak_tflops(self, iters: int = 20000) -> float:
+        out = ctypes.c_double(0.0)
+        with _torch().cuda.device(self.device):
+            rc = self.L.mpcb_dfma_peak(int(iters), ctypes.byref(out))
+        if rc != 0:
+            raise RuntimeError("mpcb_dfma_peak failed")
+        return float(out.value)
 
 
 class BatchedNlpSolver:
