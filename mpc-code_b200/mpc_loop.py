@@ -93,7 +93,25 @@ class BatchedMpc:
         self.us_k = self.u_k.clone(); self.xs_k = self.x0_m.clone()
         self.w_opt = None; self.w_guess = None
         self.dyn_status = t.zeros(self.B, dtype=t.int32, device=self.h.device)
+        self.dead = t.zeros(self.B, dtype=t.bool, device=self.h.device)
+        self.x_k0, self.dhat0, self.P0 = self.x_k.clone(), self.dhat_k.clone(), self.P_k.clone()
         self.ksim = 0
+
+    def _bury(self, bad):
+        """The reference exits the process when a state turns NaN (``MPC_code.py:671-673,819-821``).  In a batch
+        one diverged instance must not stop the others: it is flagged in ``dead`` and re-seeded with the nominal
+        initial state so that the kernels keep receiving finite numbers; its outputs are meaningless from then on."""
+        if not bool(bad.any()):
+            return
+        t = self.torch
+        self.dead |= bad
+        m = bad.unsqueeze(1)
+        self.x_k = t.where(m, self.x_k0, self.x_k)
+        self.xhat_k = t.where(m, self.x0_m, self.xhat_k)
+        self.u_k = t.where(m, self.u0, self.u_k)
+        if self.prob.nd:
+            self.dhat_k = t.where(m, self.dhat0, self.dhat_k)
+        self.P_k = t.where(m, self.P0, self.P_k)
 
     def _params(self, t_k):
         """Time-varying parameters along the horizon (``MPC_code.py:492-515``)."""
@@ -149,8 +167,7 @@ class BatchedMpc:
         else:
             self.xhat_k = xi
         out["D_HAT"] = self.dhat_k.clone()
-        if bool(t.isnan(self.xhat_k).any()):
-            raise FloatingPointError("xhat_k has some components that are NaN (MPC_code.py:671-673)")
+        self._bury(t.isnan(self.xhat_k).any(dim=1) | (t.isnan(self.dhat_k).any(dim=1) if nd else False))   # :671-673
         if p.flags["estimating"] is False:
             if p.defSP is not None:
                 ysp_k, usp_k, xsp_k = [row(v) for v in p.defSP(t_k)]
@@ -208,8 +225,8 @@ class BatchedMpc:
             self.x_k = h.plant_step(self.x_k, self.u_k, tt, row(p_xp), row(p_xmp))
         if state_noise is not None:
             self.x_k = self.x_k + h.tensor(state_noise, p.nxp)
-        if bool(t.isnan(self.x_k).any()):
-            raise FloatingPointError("x_k has some components that are NaN (MPC_code.py:819-821)")
+        self._bury(t.isnan(self.x_k).any(dim=1))                                                           # :819-821
+        out["DEAD"] = self.dead.clone()
         self.ksim += 1
         return out
 

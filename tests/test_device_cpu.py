@@ -120,3 +120,14 @@ def test_bunch_kaufman_inertia_and_solve(nmpc):
         ev = np.linalg.eigvalsh(M)
         assert inert[0] == (ev > 0).sum() and inert[1] == (ev < 0).sum() and inert[2] == 0
         assert np.abs(M @ x - b).max() < 1e-10 * np.linalg.cond(M)
+
+
+def test_closed_loop_of_device_code_matches_oracle_fixture(nmpc):
+    """Eight closed-loop steps, three instances: loop glue + device arithmetic (on the CPU) vs the oracle."""
+    from harness_loop import HarnessLoop
+    Ns, B = G["cl_noise"].shape[0], G["cl_x0"].shape[0]
+    rec = HarnessLoop(nmpc, B).run(Ns, G["cl_x0"], G["cl_noise"])
+    assert np.array_equal(rec["STATUS_DYN"], G["cl_STATUS_DYN"]) and np.array_equal(rec["ITER_DYN"], G["cl_ITER_DYN"])
+    for key in ("U", "X_HAT", "D_HAT", "XS", "US", "Xp", "Yp"):
+        assert np.abs(rec[key] - G["cl_" + key]).max() < 1e-6, key
+    assert np.all(np.abs(rec["F_DYN"] - G["cl_F_DYN"]) <= 1e-8 * np.maximum(1.0, np.abs(G["cl_F_DYN"])))
