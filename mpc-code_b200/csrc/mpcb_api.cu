@@ -51,12 +51,15 @@ __global__ void __launch_bounds__(128) k_ocp_eval(OcpArgs a) {
     ocp_eval_stage(I, a.S, k);
 }
 
-__global__ void __launch_bounds__(128) k_ocp_kkt(OcpArgs a) {
-    const int inst = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per instance (lanes over stages / matrix entries; per-warp scratch in shared memory)
+#define KKT_WARPS 4
+__global__ void __launch_bounds__(32 * KKT_WARPS) k_ocp_kkt(OcpArgs a) {
+    __shared__ double scratch[KKT_WARPS][KktScratch::total];
+    const int inst = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (inst >= a.B) return;
     if (a.st[inst].state != ST_EVAL) return;
     OcpInst I = ocp_view(a, inst);
-    ocp_kkt(I, a.S);
+    ocp_kkt(I, a.S, scratch[threadIdx.x >> 5]);
 }
 
 __global__ void __launch_bounds__(128) k_ocp_trial(OcpArgs a) {
@@ -69,14 +72,14 @@ __global__ void __launch_bounds__(128) k_ocp_trial(OcpArgs a) {
     ocp_trial_stage(I, a.S, k);
 }
 
-__global__ void __launch_bounds__(128) k_ocp_accept(OcpArgs a, int* n_active) {
-    const int inst = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(32 * KKT_WARPS) k_ocp_accept(OcpArgs a, int* n_active) {
+    const int inst = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (inst >= a.B) return;
     if (a.st[inst].state == ST_LS) {
         OcpInst I = ocp_view(a, inst);
         ocp_accept(I, a.S);
     }
-    if (a.st[inst].state != ST_DONE) atomicAdd(n_active, 1);
+    if ((threadIdx.x & 31) == 0 && a.st[inst].state != ST_DONE) atomicAdd(n_active, 1);
 }
 
 __global__ void k_ocp_output(OcpArgs a, double* f, int* status, int* iters) {
@@ -352,10 +355,10 @@ int mpcb_ocp(mpcb_handle_t h, const double* par, double* w, double* f, int* stat
     while (ticks < max_ticks) {
         for (int c = 0; c < check_every; ++c) {
             { Prof p(h, s, KC_OCP_EVAL); k_ocp_eval<<<nblk(nst, bs), bs, 0, s>>>(a); }
-            { Prof p(h, s, KC_OCP_KKT); k_ocp_kkt<<<nblk(h->B, 64), 64, 0, s>>>(a); }
+            { Prof p(h, s, KC_OCP_KKT); k_ocp_kkt<<<nblk((long)h->B * 32, 32 * KKT_WARPS), 32 * KKT_WARPS, 0, s>>>(a); }
             { Prof p(h, s, KC_OCP_TRIAL); k_ocp_trial<<<nblk(nst, bs), bs, 0, s>>>(a); }
             if (c == check_every - 1) CK(cudaMemsetAsync(h->n_active, 0, sizeof(int), s));
-            { Prof p(h, s, KC_OCP_ACCEPT); k_ocp_accept<<<nblk(h->B, 64), 64, 0, s>>>(a, h->n_active); }
+            { Prof p(h, s, KC_OCP_ACCEPT); k_ocp_accept<<<nblk((long)h->B * 32, 32 * KKT_WARPS), 32 * KKT_WARPS, 0, s>>>(a, h->n_active); }
             launches += 4; ticks++;
         }
         CK(cudaMemcpyAsync(h->h_active, h->n_active, sizeof(int), cudaMemcpyDeviceToHost, s));

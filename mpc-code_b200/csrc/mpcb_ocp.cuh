@@ -224,25 +224,64 @@ MPCB_HD void ocp_eval_stage(OcpInst& I, const OcpShared& S, int k) {
 }
 
 // =============================================================================================
-// kkt helpers
+// Lane-generic helpers.  ocp_kkt / ocp_accept are written once and run either by the 32 lanes of a
+// warp (device: one warp per instance, lanes strided over stages / matrix entries, reductions by
+// shuffle, small per-warp scratch in shared memory) or by a single "lane" on the host (tests).
 // =============================================================================================
+#ifdef __CUDA_ARCH__
+#  define LANE_ID   ((int)(threadIdx.x & 31))
+#  define N_LANES   32
+#  define W_SYNC()  __syncwarp()
+#  define W_SUM(v)  warp_sum(v)
+#  define W_MAX(v)  warp_max(v)
+#  define W_MIN(v)  warp_min(v)
+#  define W_ISUM(v) warp_sum_int(v)
+#else
+#  define LANE_ID   0
+#  define N_LANES   1
+#  define W_SYNC()
+#  define W_SUM(v)  (v)
+#  define W_MAX(v)  (v)
+#  define W_MIN(v)  (v)
+#  define W_ISUM(v) (v)
+#endif
+
+// per-warp scratch (doubles)
+struct KktScratch {
+    static constexpr int P = 0;                       // NX x NX   cost-to-go Hessian of the next stage
+    static constexpr int p = P + NX * NX;             // NX
+    static constexpr int M = p + NX;                  // NZ x NZ   condensed stage Hessian
+    static constexpr int q = M + NZ * NZ;             // NZ
+    static constexpr int T = q + NZ;                  // NX x NZ   P [A B]
+    static constexpr int f = T + NX * NZ;             // NX        P c + p
+    static constexpr int AB = f + NX;                 // NX x NZ   [A B]
+    static constexpr int K = AB + NX * NZ;            // NU x NX
+    static constexpr int kk = K + NU * NX;            // NU
+    static constexpr int sg = kk + NU;                // NGS       slack barrier curvature
+    static constexpr int cf = sg + NGS;               // NGS       slack gradient coefficient
+    static constexpr int dx = cf + NGS;               // NX
+    static constexpr int du = dx + NX;                // NU
+    static constexpr int dxn = du + NU;               // NX
+    static constexpr int total = dxn + NX;
+};
+
 // complementarity error  max |slack * z - mu|  over all bounds
 MPCB_HD double ocp_compl(const OcpInst& I, const OcpShared& S, double mu) {
     const double rf = S.o.bound_relax;
     double e = 0.0;
-    for (int i = NX; i < NW; ++i) {
+    for (int i = NX + LANE_ID; i < NW; i += N_LANES) {
         const double lo = S.lbx[i], hi = S.ubx[i];
         if (fin(lo)) e = fmax(e, fabs((I.w[i] - rlo(lo, rf)) * I.zL[i] - mu));
         if (fin(hi)) e = fmax(e, fabs((rhi(hi, rf) - I.w[i]) * I.zU[i] - mu));
     }
 #if NG > 0
-    for (int i = 0; i < NH * NG; ++i) {
+    for (int i = LANE_ID; i < NH * NG; i += N_LANES) {
         const double lo = S.lbg[i], hi = S.ubg[i];
         if (fin(lo)) e = fmax(e, fabs((I.s[i] - rlo(lo, rf)) * I.vL[i] - mu));
         if (fin(hi)) e = fmax(e, fabs((rhi(hi, rf) - I.s[i]) * I.vU[i] - mu));
     }
 #endif
-    return e;
+    return W_MAX(e);
 }
 
 struct KktErr { double dual, prim, sd, sc; };
@@ -251,7 +290,17 @@ struct KktErr { double dual, prim, sd, sc; };
 MPCB_HD KktErr ocp_errors(const OcpInst& I, const OcpShared& S) {
     double dual = 0.0, prim = 0.0, ysum = 0.0, zsum = 0.0;
     int nb = 0;
-    for (int k = 0; k < NH; ++k) {
+    for (int k = LANE_ID; k <= NH; k += N_LANES) {
+        if (k == NH) {                                            // terminal state
+            for (int j = 0; j < NX; ++j) {
+                const int wi = NH * NZ + j;
+                const double r = I.gN[j] - I.lam[(NH - 1) * NX + j] + I.zU[wi] - I.zL[wi];
+                dual = fmax(dual, fabs(r));
+                zsum += I.zL[wi] + I.zU[wi];
+                nb += (fin(S.lbx[wi]) ? 1 : 0) + (fin(S.ubx[wi]) ? 1 : 0);
+            }
+            continue;
+        }
         const double* A = I.A + k * NX * NX; const double* Bm = I.Bm + k * NX * NU;
         const double* lamn = I.lam + k * NX;                  // lam_{k+1}
         for (int j = 0; j < NZ; ++j) {
@@ -281,13 +330,7 @@ MPCB_HD KktErr ocp_errors(const OcpInst& I, const OcpShared& S) {
         }
 #endif
     }
-    for (int j = 0; j < NX; ++j) {
-        const int wi = NH * NZ + j;
-        const double r = I.gN[j] - I.lam[(NH - 1) * NX + j] + I.zU[wi] - I.zL[wi];
-        dual = fmax(dual, fabs(r));
-        zsum += I.zL[wi] + I.zU[wi];
-        nb += (fin(S.lbx[wi]) ? 1 : 0) + (fin(S.ubx[wi]) ? 1 : 0);
-    }
+    dual = W_MAX(dual); prim = W_MAX(prim); ysum = W_SUM(ysum); zsum = W_SUM(zsum); nb = W_ISUM(nb);
     const double smax = 100.0;
     const int mc = NH * NX + NH * NG;
     KktErr e;
@@ -298,87 +341,108 @@ MPCB_HD KktErr ocp_errors(const OcpInst& I, const OcpShared& S) {
 }
 
 // Riccati backward sweep with regularisation dw on every primal variable.  Returns false when some
-// R_k + B_k' P_{k+1} B_k is not positive definite (wrong inertia).
-MPCB_HD bool ocp_riccati(OcpInst& I, const OcpShared& S, double mu, double dwreg) {
+// R_k + B_k' P_{k+1} B_k is not positive definite (wrong inertia).  `sm` is the per-warp scratch.
+MPCB_HD bool ocp_riccati(OcpInst& I, const OcpShared& S, double mu, double dwreg, double* sm) {
     const double rf = S.o.bound_relax;
-    double P[NX * NX], p[NX];
+    const int lane = LANE_ID;
+    double* P = sm + KktScratch::P; double* p = sm + KktScratch::p; double* M = sm + KktScratch::M;
+    double* q = sm + KktScratch::q; double* T = sm + KktScratch::T; double* f = sm + KktScratch::f;
+    double* AB = sm + KktScratch::AB; double* Kk = sm + KktScratch::K; double* kk = sm + KktScratch::kk;
+    double* sg = sm + KktScratch::sg; double* cf = sm + KktScratch::cf;
     // terminal stage
-    for (int i = 0; i < NX; ++i) {
+    for (int e = lane; e < NX * NX; e += N_LANES) {
+        const int i = e % NX, j = e / NX;
+        double v = I.HN[tri(i, j)];
+        if (i == j) {
+            const int wi = NH * NZ + i;
+            const double lo = S.lbx[wi], hi = S.ubx[wi];
+            v += dwreg;
+            if (fin(lo)) v += I.zL[wi] / (I.w[wi] - rlo(lo, rf));
+            if (fin(hi)) v += I.zU[wi] / (rhi(hi, rf) - I.w[wi]);
+        }
+        P[e] = v;
+        I.Pm[NH * NX * NX + e] = v;
+    }
+    for (int i = lane; i < NX; i += N_LANES) {
         const int wi = NH * NZ + i;
         const double lo = S.lbx[wi], hi = S.ubx[wi];
-        double sig = dwreg, q = I.gN[i];
-        if (fin(lo)) { const double dl = I.w[wi] - rlo(lo, rf); sig += I.zL[wi] / dl; q -= mu / dl; }
-        if (fin(hi)) { const double du = rhi(hi, rf) - I.w[wi]; sig += I.zU[wi] / du; q += mu / du; }
-        for (int j = 0; j < NX; ++j) P[i + NX * j] = I.HN[tri(i, j)];
-        P[i + NX * i] += sig;
-        p[i] = q;
+        double qv = I.gN[i];
+        if (fin(lo)) qv -= mu / (I.w[wi] - rlo(lo, rf));
+        if (fin(hi)) qv += mu / (rhi(hi, rf) - I.w[wi]);
+        p[i] = qv;
+        I.pv[NH * NX + i] = qv;
     }
-    for (int i = 0; i < NX * NX; ++i) I.Pm[NH * NX * NX + i] = P[i];
-    for (int i = 0; i < NX; ++i) I.pv[NH * NX + i] = p[i];
+    W_SYNC();
     for (int k = NH - 1; k >= 0; --k) {
-        const double* A = I.A + k * NX * NX; const double* Bm = I.Bm + k * NX * NU;
-        double M[NZ * NZ], q[NZ];
-        // condensed stage Hessian and gradient
-        for (int i = 0; i < NZ; ++i) {
-            for (int j = 0; j < NZ; ++j) M[i + NZ * j] = I.H[k * NZP + tri(i, j)];
-            q[i] = I.gl[k * NZ + i];
-        }
-        for (int j = 0; j < NZ; ++j) {
-            M[j + NZ * j] += dwreg;
-            if (k == 0 && j < NX) continue;
-            const int wi = k * NZ + j;
-            const double lo = S.lbx[wi], hi = S.ubx[wi];
-            if (fin(lo)) { const double dl = I.w[wi] - rlo(lo, rf); M[j + NZ * j] += I.zL[wi] / dl; q[j] -= mu / dl; }
-            if (fin(hi)) { const double du = rhi(hi, rf) - I.w[wi]; M[j + NZ * j] += I.zU[wi] / du; q[j] += mu / du; }
-        }
+        // ---- (a) load [A B]; slack barrier terms of the range rows
+        for (int e = lane; e < NX * NZ; e += N_LANES)
+            AB[e] = (e < NX * NX) ? I.A[k * NX * NX + e] : I.Bm[k * NX * NU + (e - NX * NX)];
 #if NG > 0
-        for (int r = 0; r < NG; ++r) {
+        for (int r = lane; r < NG; r += N_LANES) {
             const int gi = k * NG + r;
             const double lo = S.lbg[gi], hi = S.ubg[gi];
             double sig = dwreg, b = 0.0;
             if (fin(lo)) { const double dl = I.s[gi] - rlo(lo, rf); sig += I.vL[gi] / dl; b -= mu / dl; }
             if (fin(hi)) { const double du = rhi(hi, rf) - I.s[gi]; sig += I.vU[gi] / du; b += mu / du; }
-            const double rg = I.gv[gi] - I.s[gi];
-            const double coef = sig * rg + b;
-            const double* Gr = I.G + k * NG * NZ + r;       // row r of G (column-major NG x NZ)
-            for (int i = 0; i < NZ; ++i) {
-                q[i] += Gr[NG * i] * coef;
-                for (int j = 0; j < NZ; ++j) M[i + NZ * j] += Gr[NG * i] * sig * Gr[NG * j];
-            }
+            sg[r] = sig;
+            cf[r] = sig * (I.gv[gi] - I.s[gi]) + b;
         }
 #endif
-        // f = P c + p ;  M += [A B]' P [A B] ;  q += [A B]' f
-        double f[NX], T[NX * NZ];
-        for (int i = 0; i < NX; ++i) {
+        W_SYNC();
+        // ---- (b) f = P c + p ;  T = P [A B]
+        for (int i = lane; i < NX; i += N_LANES) {
             double a = p[i];
             for (int j = 0; j < NX; ++j) a += P[i + NX * j] * I.c[k * NX + j];
             f[i] = a;
         }
-        for (int j = 0; j < NZ; ++j) {
-            const double* col = (j < NX) ? (A + NX * j) : (Bm + NX * (j - NX));
-            for (int i = 0; i < NX; ++i) {
-                double a = 0.0;
-                for (int l = 0; l < NX; ++l) a += P[i + NX * l] * col[l];
-                T[i + NX * j] = a;
-            }
-        }
-        for (int i = 0; i < NZ; ++i) {
-            const double* coli = (i < NX) ? (A + NX * i) : (Bm + NX * (i - NX));
+        for (int e = lane; e < NX * NZ; e += N_LANES) {
+            const int i = e % NX, j = e / NX;
             double a = 0.0;
-            for (int l = 0; l < NX; ++l) a += coli[l] * f[l];
-            q[i] += a;
-            for (int j = 0; j < NZ; ++j) {
-                double m = 0.0;
-                for (int l = 0; l < NX; ++l) m += coli[l] * T[l + NX * j];
-                M[i + NZ * j] += m;
-            }
+            for (int l = 0; l < NX; ++l) a += P[i + NX * l] * AB[l + NX * j];
+            T[e] = a;
         }
-        // Cholesky of the input block M_uu = L L'
+        W_SYNC();
+        // ---- (c) condensed stage Hessian M and gradient q, plus [A B]' P [A B] and [A B]' f
+        for (int e = lane; e < NZ * NZ; e += N_LANES) {
+            const int i = e % NZ, j = e / NZ;
+            double m = I.H[k * NZP + tri(i, j)];
+            if (i == j) {
+                m += dwreg;
+                if (!(k == 0 && j < NX)) {
+                    const int wi = k * NZ + j;
+                    const double lo = S.lbx[wi], hi = S.ubx[wi];
+                    if (fin(lo)) m += I.zL[wi] / (I.w[wi] - rlo(lo, rf));
+                    if (fin(hi)) m += I.zU[wi] / (rhi(hi, rf) - I.w[wi]);
+                }
+            }
+#if NG > 0
+            for (int r = 0; r < NG; ++r) m += I.G[k * NG * NZ + r + NG * i] * sg[r] * I.G[k * NG * NZ + r + NG * j];
+#endif
+            for (int l = 0; l < NX; ++l) m += AB[l + NX * i] * T[l + NX * j];
+            M[e] = m;
+        }
+        for (int i = lane; i < NZ; i += N_LANES) {
+            double a = I.gl[k * NZ + i];
+            if (!(k == 0 && i < NX)) {
+                const int wi = k * NZ + i;
+                const double lo = S.lbx[wi], hi = S.ubx[wi];
+                if (fin(lo)) a -= mu / (I.w[wi] - rlo(lo, rf));
+                if (fin(hi)) a += mu / (rhi(hi, rf) - I.w[wi]);
+            }
+#if NG > 0
+            for (int r = 0; r < NG; ++r) a += I.G[k * NG * NZ + r + NG * i] * cf[r];
+#endif
+            for (int l = 0; l < NX; ++l) a += AB[l + NX * i] * f[l];
+            q[i] = a;
+        }
+        W_SYNC();
+        // ---- (d) Cholesky of the input block M_uu = L L' (every lane, in registers)
         double L[NU * NU];
+        bool pd = true;
         for (int j = 0; j < NU; ++j) {
             double djj = M[(NX + j) + NZ * (NX + j)];
             for (int l = 0; l < j; ++l) djj -= L[j + NU * l] * L[j + NU * l];
-            if (!(djj > 0.0)) return false;
+            if (!(djj > 0.0)) { pd = false; djj = 1.0; }
             djj = sqrt(djj);
             L[j + NU * j] = djj;
             for (int i = j + 1; i < NU; ++i) {
@@ -387,9 +451,9 @@ MPCB_HD bool ocp_riccati(OcpInst& I, const OcpShared& S, double mu, double dwreg
                 L[i + NU * j] = a / djj;
             }
         }
-        // K = -Muu^{-1} Mux (NU x NX), kff = -Muu^{-1} q_u
-        double Kk[NU * NX], kk[NU];
-        for (int c = 0; c <= NX; ++c) {
+        if (!pd) return false;                                   // uniform across the warp
+        // ---- (e) K = -Muu^{-1} Mux (NU x NX), kff = -Muu^{-1} q_u : one column per lane
+        for (int c = lane; c <= NX; c += N_LANES) {
             double y[NU];
             for (int i = 0; i < NU; ++i) {
                 double a = (c < NX) ? M[(NX + i) + NZ * c] : q[NX + i];
@@ -401,73 +465,83 @@ MPCB_HD bool ocp_riccati(OcpInst& I, const OcpShared& S, double mu, double dwreg
                 for (int l = i + 1; l < NU; ++l) a -= L[l + NU * i] * y[l];
                 y[i] = a / L[i + NU * i];
             }
-            for (int i = 0; i < NU; ++i) { if (c < NX) Kk[i + NU * c] = -y[i]; else kk[i] = -y[i]; }
+            for (int i = 0; i < NU; ++i) {
+                if (c < NX) { Kk[i + NU * c] = -y[i]; I.Kf[k * NU * NX + i + NU * c] = -y[i]; }
+                else { kk[i] = -y[i]; I.kf[k * NU + i] = -y[i]; }
+            }
         }
-        // P = Mxx + Mxu K (symmetrised), p = q_x + Mxu kff
-        for (int i = 0; i < NX; ++i) {
+        W_SYNC();
+        // ---- (f) P = Mxx + Mxu K (symmetrised), p = q_x + Mxu kff
+        for (int e = lane; e < NX * NX; e += N_LANES) {
+            const int i = e % NX, j = e / NX;
+            double a = M[i + NZ * j], b = M[j + NZ * i];
+            for (int l = 0; l < NU; ++l) { a += M[i + NZ * (NX + l)] * Kk[l + NU * j]; b += M[j + NZ * (NX + l)] * Kk[l + NU * i]; }
+            const double v = (i == j) ? a : 0.5 * (a + b);
+            P[e] = v;
+            I.Pm[k * NX * NX + e] = v;
+        }
+        for (int i = lane; i < NX; i += N_LANES) {
             double a = q[i];
             for (int l = 0; l < NU; ++l) a += M[i + NZ * (NX + l)] * kk[l];
             p[i] = a;
-            for (int j = 0; j < NX; ++j) {
-                double m = M[i + NZ * j];
-                for (int l = 0; l < NU; ++l) m += M[i + NZ * (NX + l)] * Kk[l + NU * j];
-                P[i + NX * j] = m;
-            }
+            I.pv[k * NX + i] = a;
         }
-        for (int i = 0; i < NX; ++i)
-            for (int j = 0; j < i; ++j) { const double m = 0.5 * (P[i + NX * j] + P[j + NX * i]); P[i + NX * j] = m; P[j + NX * i] = m; }
-        for (int i = 0; i < NX * NX; ++i) I.Pm[k * NX * NX + i] = P[i];
-        for (int i = 0; i < NX; ++i) I.pv[k * NX + i] = p[i];
-        for (int i = 0; i < NU * NX; ++i) I.Kf[k * NU * NX + i] = Kk[i];
-        for (int i = 0; i < NU; ++i) I.kf[k * NU + i] = kk[i];
+        W_SYNC();
     }
     return true;
 }
 
 MPCB_HD void ocp_finish(OcpInst& I, const OcpShared& S, int status) {
     InstState& st = *I.st;
-    st.status = status;
-    st.state = ST_DONE;
     double f = 0.0;
-    for (int k = 0; k <= NH; ++k) f += I.part[k * 4 + 0];
-    st.fval = f;
+    for (int k = LANE_ID; k <= NH; k += N_LANES) f += I.part[k * 4 + 0];
+    f = W_SUM(f);
     if (S.o.honor_original_bounds)
-        for (int i = NX; i < NW; ++i) I.w[i] = fmin(fmax(I.w[i], S.lbx[i]), S.ubx[i]);
+        for (int i = NX + LANE_ID; i < NW; i += N_LANES) I.w[i] = fmin(fmax(I.w[i], S.lbx[i]), S.ubx[i]);
+    if (LANE_ID == 0) { st.status = status; st.state = ST_DONE; st.fval = f; }
+    W_SYNC();
 }
 
 // =============================================================================================
 // kkt: one interior-point iteration up to (not including) the line search, for one instance
 // =============================================================================================
-MPCB_HD void ocp_kkt(OcpInst& I, const OcpShared& S) {
+MPCB_HD void ocp_kkt(OcpInst& I, const OcpShared& S, double* sm) {
     InstState& st = *I.st;
     const double rf = S.o.bound_relax;
+    const int lane = LANE_ID;
+    const int iter = st.iter;
 #if NG > 0
     // A stage-0 range row that does not depend on u_0 is a constant (x_0 is fixed).  Outside its relaxed
     // bounds the OCP is infeasible: IPOPT would end in restoration with Infeasible_Problem_Detected, the
     // one status the reference loop reacts to (MPC_code.py:786,804; quirk D7 of SURVEY.md).
-    if (st.iter == 0) {
+    if (iter == 0) {
+        bool infeasible = false;
         for (int r = 0; r < NG; ++r) {
             bool constant = true;
             for (int j = NX; j < NZ; ++j) if (I.G[r + NG * j] != 0.0) constant = false;
             if (!constant) continue;
             const double v = I.gv[r], lo = S.lbg[r], hi = S.ubg[r];
-            if ((fin(lo) && v < rlo(lo, rf) - S.o.tol) || (fin(hi) && v > rhi(hi, rf) + S.o.tol)) { ocp_finish(I, S, 2); return; }
+            if ((fin(lo) && v < rlo(lo, rf) - S.o.tol) || (fin(hi) && v > rhi(hi, rf) + S.o.tol)) infeasible = true;
         }
+        if (infeasible) { ocp_finish(I, S, 2); return; }
     }
 #endif
     // ---- optimality error and termination (IPOPT: tol, dual_inf_tol=1, constr_viol_tol=1e-4, compl_inf_tol=1e-4)
     const KktErr e = ocp_errors(I, S);
     const double c0 = ocp_compl(I, S, 0.0);
     const double E0 = fmax(fmax(e.dual / e.sd, e.prim), c0 / e.sc);
-    st.E0 = E0;
+    int acc_cnt = st.acc_cnt;
+    W_SYNC();
+    if (lane == 0) st.E0 = E0;
     if (!(E0 == E0) || !fin(E0)) { ocp_finish(I, S, -13); return; }
     if (E0 <= S.o.tol && e.dual <= 1.0 && e.prim <= 1e-4 && c0 <= 1e-4) { ocp_finish(I, S, 0); return; }
     if (E0 <= S.o.acceptable_tol && e.dual <= 1e10 && e.prim <= 1e-2 && c0 <= 1e-2) {
-        if (++st.acc_cnt >= S.o.acceptable_iter) { ocp_finish(I, S, 1); return; }
+        acc_cnt += 1;
+        if (acc_cnt >= S.o.acceptable_iter) { ocp_finish(I, S, 1); return; }
     } else {
-        st.acc_cnt = 0;
+        acc_cnt = 0;
     }
-    if (st.iter >= S.o.max_iter) { ocp_finish(I, S, -1); return; }
+    if (iter >= S.o.max_iter) { ocp_finish(I, S, -1); return; }
     // ---- monotone barrier update (kappa_eps=10, kappa_mu=0.2, theta_mu=1.5)
     double mu = st.mu;
     const double mu_min = S.o.tol / 10.0;
@@ -478,75 +552,82 @@ MPCB_HD void ocp_kkt(OcpInst& I, const OcpShared& S) {
         mu = fmax(mu_min, fmin(0.2 * mu, pow(mu, 1.5)));
         changed = true;
     }
-    if (changed) { st.mu = mu; st.tau = fmax(0.99, 1.0 - mu); st.nfilt = 0; }
-    const double tau = st.tau;
+    const double tau = changed ? fmax(0.99, 1.0 - mu) : st.tau;
+    const double dw_last = st.dw_last;
+    const double theta0_old = st.theta0;
+    W_SYNC();
     // ---- Newton step by Riccati recursion, inertia-correcting ladder on delta_w
     double dwreg = 0.0;
     bool first = true, ok = false;
     for (int attempt = 0; attempt < 60; ++attempt) {
-        if (ocp_riccati(I, S, mu, dwreg)) { ok = true; break; }
-        if (first) { dwreg = (st.dw_last == 0.0) ? 1e-4 : fmax(1e-20, st.dw_last / 3.0); first = false; }
-        else dwreg *= (st.dw_last == 0.0) ? 100.0 : 8.0;
+        if (ocp_riccati(I, S, mu, dwreg, sm)) { ok = true; break; }
+        W_SYNC();
+        if (first) { dwreg = (dw_last == 0.0) ? 1e-4 : fmax(1e-20, dw_last / 3.0); first = false; }
+        else dwreg *= (dw_last == 0.0) ? 100.0 : 8.0;
         if (dwreg > 1e40) break;
     }
     if (!ok) { ocp_finish(I, S, -3); return; }
-    if (dwreg > 0.0) st.dw_last = dwreg;
-    // ---- forward sweep: dw, new multipliers; slack / multiplier steps of the range rows
-    double dx[NX];
-    for (int i = 0; i < NX; ++i) { dx[i] = 0.0; I.dw[i] = 0.0; }
-    double amax = 1.0, az = 1.0, gphid = 0.0, theta = 0.0, barr = 0.0, fobj = 0.0;
+    // ---- forward sweep (sequential over the stages): dw and the new dynamics multipliers
+    double* dx = sm + KktScratch::dx; double* du = sm + KktScratch::du; double* dxn = sm + KktScratch::dxn;
+    for (int i = lane; i < NX; i += N_LANES) { dx[i] = 0.0; I.dw[i] = 0.0; }
+    W_SYNC();
     for (int k = 0; k < NH; ++k) {
         const double* A = I.A + k * NX * NX; const double* Bm = I.Bm + k * NX * NU;
-        double du[NU], dxn[NX];
-        for (int i = 0; i < NU; ++i) {
+        for (int i = lane; i < NU; i += N_LANES) {
             double a = I.kf[k * NU + i];
             for (int j = 0; j < NX; ++j) a += I.Kf[k * NU * NX + i + NU * j] * dx[j];
             du[i] = a;
             I.dw[k * NZ + NX + i] = a;
         }
-        for (int i = 0; i < NX; ++i) {
+        W_SYNC();
+        for (int i = lane; i < NX; i += N_LANES) {
             double a = I.c[k * NX + i];
             for (int j = 0; j < NX; ++j) a += A[i + NX * j] * dx[j];
             for (int j = 0; j < NU; ++j) a += Bm[i + NX * j] * du[j];
             dxn[i] = a;
             I.dw[(k + 1) * NZ + i] = a;
         }
-        for (int i = 0; i < NX; ++i) {
+        W_SYNC();
+        for (int i = lane; i < NX; i += N_LANES) {
             double a = I.pv[(k + 1) * NX + i];
             for (int j = 0; j < NX; ++j) a += I.Pm[(k + 1) * NX * NX + i + NX * j] * dxn[j];
             I.lamn[k * NX + i] = a;
+            dx[i] = dxn[i];
         }
+        W_SYNC();
+    }
+    // ---- stage-parallel: slack / multiplier steps of the range rows, fraction to the boundary (primal and
+    //      dual), barrier objective and its directional derivative
+    double amax = 1.0, az = 1.0, gphid = 0.0, theta = 0.0, barr = 0.0, fobj = 0.0;
+    for (int k = lane; k <= NH; k += N_LANES) {
+        fobj += I.part[k * 4 + 0];
+        if (k < NH) theta += I.part[k * 4 + 1];
 #if NG > 0
-        for (int r = 0; r < NG; ++r) {
-            const int gi = k * NG + r;
-            const double lo = S.lbg[gi], hi = S.ubg[gi];
-            double sig = dwreg, b = 0.0, dl = 1.0, du_ = 1.0;
-            if (fin(lo)) { dl = I.s[gi] - rlo(lo, rf); sig += I.vL[gi] / dl; b -= mu / dl; barr += log(dl); }
-            if (fin(hi)) { du_ = rhi(hi, rf) - I.s[gi]; sig += I.vU[gi] / du_; b += mu / du_; barr += log(du_); }
-            double dsr = I.gv[gi] - I.s[gi];
-            for (int j = 0; j < NZ; ++j) dsr += I.G[k * NG * NZ + r + NG * j] * ((j < NX) ? dx[j] : du[j - NX]);
-            I.ds[gi] = dsr;
-            I.dym[gi] = sig * dsr + b - I.ym[gi];
-            gphid += b * dsr;
-            if (fin(lo)) {
-                if (dsr < 0.0) amax = fmin(amax, -tau * dl / dsr);
-                const double dz = mu / dl - I.vL[gi] - I.vL[gi] / dl * dsr;
-                if (dz < 0.0) az = fmin(az, -tau * I.vL[gi] / dz);
-            }
-            if (fin(hi)) {
-                if (dsr > 0.0) amax = fmin(amax, tau * du_ / dsr);
-                const double dz = mu / du_ - I.vU[gi] + I.vU[gi] / du_ * dsr;
-                if (dz < 0.0) az = fmin(az, -tau * I.vU[gi] / dz);
+        if (k < NH) {
+            for (int r = 0; r < NG; ++r) {
+                const int gi = k * NG + r;
+                const double lo = S.lbg[gi], hi = S.ubg[gi];
+                double sig = dwreg, b = 0.0, dl = 1.0, du_ = 1.0;
+                if (fin(lo)) { dl = I.s[gi] - rlo(lo, rf); sig += I.vL[gi] / dl; b -= mu / dl; barr += log(dl); }
+                if (fin(hi)) { du_ = rhi(hi, rf) - I.s[gi]; sig += I.vU[gi] / du_; b += mu / du_; barr += log(du_); }
+                double dsr = I.gv[gi] - I.s[gi];
+                for (int j = 0; j < NZ; ++j) dsr += I.G[k * NG * NZ + r + NG * j] * I.dw[k * NZ + j];
+                I.ds[gi] = dsr;
+                I.dym[gi] = sig * dsr + b - I.ym[gi];
+                gphid += b * dsr;
+                if (fin(lo)) {
+                    if (dsr < 0.0) amax = fmin(amax, -tau * dl / dsr);
+                    const double dz = mu / dl - I.vL[gi] - I.vL[gi] / dl * dsr;
+                    if (dz < 0.0) az = fmin(az, -tau * I.vL[gi] / dz);
+                }
+                if (fin(hi)) {
+                    if (dsr > 0.0) amax = fmin(amax, tau * du_ / dsr);
+                    const double dz = mu / du_ - I.vU[gi] + I.vU[gi] / du_ * dsr;
+                    if (dz < 0.0) az = fmin(az, -tau * I.vU[gi] / dz);
+                }
             }
         }
 #endif
-        for (int i = 0; i < NX; ++i) dx[i] = dxn[i];
-        theta += I.part[k * 4 + 1];
-        fobj += I.part[k * 4 + 0];
-    }
-    fobj += I.part[NH * 4 + 0];
-    // ---- fraction to the boundary (primal and dual), barrier objective and its directional derivative
-    for (int k = 0; k <= NH; ++k) {
         const int nz = (k == NH) ? NX : NZ;
         for (int j = 0; j < nz; ++j) {
             if (k == 0 && j < NX) continue;
@@ -570,9 +651,10 @@ MPCB_HD void ocp_kkt(OcpInst& I, const OcpShared& S) {
             }
         }
     }
+    amax = W_MIN(amax); az = W_MIN(az); gphid = W_SUM(gphid); theta = W_SUM(theta); barr = W_SUM(barr); fobj = W_SUM(fobj);
     const double phi = fobj - mu * barr;
-    if (st.theta0 < 0.0) st.theta0 = theta;
-    const double theta_min = 1e-4 * fmax(1.0, st.theta0);
+    const double theta0 = (theta0_old < 0.0) ? theta : theta0_old;
+    const double theta_min = 1e-4 * fmax(1.0, theta0);
     // minimal step size before the line search gives up (gamma_alpha=0.05, gamma_theta=1e-5, gamma_phi=1e-8)
     double amin;
     if (gphid < 0.0 && theta <= theta_min) {
@@ -582,11 +664,18 @@ MPCB_HD void ocp_kkt(OcpInst& I, const OcpShared& S) {
     } else {
         amin = 1e-5;
     }
-    st.amin = 0.05 * amin;
-    st.theta = theta; st.phi = phi; st.gphid = gphid;
-    st.alpha = amax; st.alpha_z = az;
-    st.ls_iter = 0;
-    st.state = ST_LS;
+    if (lane == 0) {
+        st.acc_cnt = acc_cnt;
+        if (changed) { st.mu = mu; st.tau = tau; st.nfilt = 0; }
+        if (dwreg > 0.0) st.dw_last = dwreg;
+        st.theta0 = theta0;
+        st.amin = 0.05 * amin;
+        st.theta = theta; st.phi = phi; st.gphid = gphid;
+        st.alpha = amax; st.alpha_z = az;
+        st.ls_iter = 0;
+        st.state = ST_LS;
+    }
+    W_SYNC();
 }
 
 // =============================================================================================
@@ -643,19 +732,22 @@ MPCB_HD void ocp_trial_stage(OcpInst& I, const OcpShared& S, int k) {
 }
 
 // =============================================================================================
-// accept: filter line-search decision for one instance
+// accept: filter line-search decision for one instance (lane-generic, see above)
 // =============================================================================================
 MPCB_HD void ocp_accept(OcpInst& I, const OcpShared& S) {
     InstState& st = *I.st;
+    const int lane = LANE_ID;
     const double rf = S.o.bound_relax, mu = st.mu;
     double th_t = 0.0, f_t = 0.0, b_t = 0.0;
-    for (int k = 0; k <= NH; ++k) { f_t += I.partt[k * 4 + 0]; th_t += I.partt[k * 4 + 1]; b_t += I.partt[k * 4 + 2]; }
+    for (int k = lane; k <= NH; k += N_LANES) { f_t += I.partt[k * 4 + 0]; th_t += I.partt[k * 4 + 1]; b_t += I.partt[k * 4 + 2]; }
+    th_t = W_SUM(th_t); f_t = W_SUM(f_t); b_t = W_SUM(b_t);
     const double ph_t = f_t - mu * b_t;
-    const double theta = st.theta, phi = st.phi, gphid = st.gphid, alpha = st.alpha;
+    const double theta = st.theta, phi = st.phi, gphid = st.gphid, alpha = st.alpha, az = st.alpha_z;
     const double theta_min = 1e-4 * fmax(1.0, st.theta0), theta_max = 1e4 * fmax(1.0, st.theta0);
+    const int nfilt = st.nfilt;
     bool ok = (th_t == th_t) && (ph_t == ph_t) && fin(th_t) && fin(ph_t) && th_t <= theta_max;
     if (ok)
-        for (int i = 0; i < st.nfilt; ++i)
+        for (int i = 0; i < nfilt; ++i)
             if (th_t >= st.filt[2 * i] && ph_t >= st.filt[2 * i + 1]) { ok = false; break; }
     bool accepted = false, ftype = false;
     if (ok) {
@@ -667,20 +759,19 @@ MPCB_HD void ocp_accept(OcpInst& I, const OcpShared& S) {
             if (th_t <= (1.0 - 1e-5) * theta || ph_t - eps <= phi - 1e-8 * theta) accepted = true;
         }
     }
+    const double amin = st.amin;
+    W_SYNC();
     if (!accepted) {
-        st.alpha = 0.5 * alpha;
-        st.ls_iter += 1;
-        if (!(st.alpha >= st.amin * (1.0 - 1e-12)) || st.alpha <= 1e-16) ocp_finish(I, S, -2);   // no restoration phase
+        const double an = 0.5 * alpha;
+        const bool give_up = !(an >= amin * (1.0 - 1e-12)) || an <= 1e-16;
+        if (lane == 0) { st.alpha = an; st.ls_iter += 1; }
+        W_SYNC();
+        if (give_up) ocp_finish(I, S, -2);                      // no restoration phase
         return;
     }
-    if (!ftype && st.nfilt < MPCB_MAXFILT) {
-        st.filt[2 * st.nfilt] = (1.0 - 1e-5) * theta;
-        st.filt[2 * st.nfilt + 1] = phi - 1e-8 * theta;
-        st.nfilt += 1;
-    }
     // ---- take the step; bound multipliers with their own step size, then the kappa_sigma safeguard
-    const double az = st.alpha_z, ks = 1e10;
-    for (int i = NX; i < NW; ++i) {
+    const double ks = 1e10;
+    for (int i = NX + lane; i < NW; i += N_LANES) {
         const double lo = S.lbx[i], hi = S.ubx[i], dv = I.dw[i];
         const double wn = I.w[i] + alpha * dv;
         if (fin(lo)) {
@@ -695,9 +786,9 @@ MPCB_HD void ocp_accept(OcpInst& I, const OcpShared& S) {
         }
         I.w[i] = wn;
     }
-    for (int i = 0; i < NH * NX; ++i) I.lam[i] += alpha * (I.lamn[i] - I.lam[i]);
+    for (int i = lane; i < NH * NX; i += N_LANES) I.lam[i] += alpha * (I.lamn[i] - I.lam[i]);
 #if NG > 0
-    for (int i = 0; i < NH * NG; ++i) {
+    for (int i = lane; i < NH * NG; i += N_LANES) {
         const double lo = S.lbg[i], hi = S.ubg[i], dv = I.ds[i];
         const double sn = I.s[i] + alpha * dv;
         if (fin(lo)) {
@@ -714,6 +805,14 @@ MPCB_HD void ocp_accept(OcpInst& I, const OcpShared& S) {
         I.ym[i] += alpha * I.dym[i];
     }
 #endif
-    st.iter += 1;
-    st.state = ST_EVAL;
+    if (lane == 0) {
+        if (!ftype && nfilt < MPCB_MAXFILT) {
+            st.filt[2 * nfilt] = (1.0 - 1e-5) * theta;
+            st.filt[2 * nfilt + 1] = phi - 1e-8 * theta;
+            st.nfilt = nfilt + 1;
+        }
+        st.iter += 1;
+        st.state = ST_EVAL;
+    }
+    W_SYNC();
 }

@@ -70,7 +70,8 @@ int h_ocp(int B, const double* par, double* w, double* f, int* status, int* iter
         int active = 0;
         for (int inst = 0; inst < B; ++inst) {
             OcpInst I = view(inst);
-            if (st[inst].state == ST_EVAL) { for (int k = 0; k < NH; ++k) ocp_eval_stage(I, S, k); ocp_kkt(I, S); }
+            double scratch[KktScratch::total];
+            if (st[inst].state == ST_EVAL) { for (int k = 0; k < NH; ++k) ocp_eval_stage(I, S, k); ocp_kkt(I, S, scratch); }
             if (st[inst].state == ST_LS) { for (int k = 0; k < NH; ++k) ocp_trial_stage(I, S, k); ocp_accept(I, S); }
             if (st[inst].state != ST_DONE) active++;
         }
