@@ -246,13 +246,11 @@ def run_gpu(args):
     replay_err = float((u_host[W:].to(dev) - torch.stack(us[W:])).abs().max().item())
 
     # ---------------- statistics gathered over NCCL (the only collective; off the timed path) ----------------
-    st_dyn = torch.stack([s[0] for s in stat]); it_dyn = torch.stack([s[1] for s in stat]).double()
-    counts = torch.tensor([(st_dyn == 0).sum(), (st_dyn == 1).sum(), (st_dyn == 2).sum(), (st_dyn < 0).sum(),
-                           it_dyn.sum(), float(st_dyn.numel())], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(counts)
-        gathered = [torch.empty_like(us[-1]) for _ in range(world)]
-        dist.all_gather(gathered, us[-1].contiguous())               # closed-loop inputs of the last step, all ranks
+    from mpc_code_b200.sharding import gather_instances, reduce_stats
+    st_dyn = torch.stack([s[0] for s in stat]); it_dyn = torch.stack([s[1] for s in stat])
+    stats = reduce_stats(st_dyn, it_dyn)
+    u_all = gather_instances(torch.stack(us[W:]), world * B)         # closed-loop inputs of all ranks, [K, N*B, nu]
+    assert u_all.shape[1] == world * B
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -295,7 +293,6 @@ def run_gpu(args):
                         "sample": "%d instances x 2 closed-loop steps of the same workload, one process per core (%.1f s); "
                                   "dense-KKT oracle port, not IPOPT" % (cores, wall)}
     clocks = _parse_clocks(clock_file, local)
-    n_inst = counts[5].item()
     out = {
         "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": elapsed_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -309,9 +306,7 @@ def run_gpu(args):
                 "replay_max_abs_du": replay_err},
         "gpu_launches": int(launches),
         "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
-        "solver_stats": {"solve_succeeded": counts[0].item() / n_inst, "acceptable": counts[1].item() / n_inst,
-                         "infeasible": counts[2].item() / n_inst, "failed": counts[3].item() / n_inst,
-                         "mean_ipm_iterations": counts[4].item() / n_inst},
+        "solver_stats": stats,
     }
     print(json.dumps(out))
     if world > 1:

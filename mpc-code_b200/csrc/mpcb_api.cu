@@ -14,6 +14,14 @@
 #define MPCB_NKERNELS 8
 enum { KC_OCP_INIT = 0, KC_OCP_EVAL = 1, KC_OCP_KKT = 2, KC_OCP_TRIAL = 3, KC_OCP_ACCEPT = 4, KC_TARGET = 5, KC_ESTIMATE = 6, KC_OTHER = 7 };
 
+// launch shape of the stage-parallel kernels (tunable at build time: tools/tune_eval.py)
+#ifndef MPCB_EVAL_BLOCK
+#define MPCB_EVAL_BLOCK 128
+#endif
+#ifndef MPCB_EVAL_MINBLOCKS
+#define MPCB_EVAL_MINBLOCKS 2
+#endif
+
 #ifndef MPCB_FLOPS_TABLE
 #define MPCB_FLOPS_TABLE
 #endif
@@ -41,7 +49,7 @@ __global__ void __launch_bounds__(128) k_ocp_init(OcpArgs a) {
     ocp_init_stage(I, a.S, k);
 }
 
-__global__ void __launch_bounds__(128) k_ocp_eval(OcpArgs a) {
+__global__ void __launch_bounds__(MPCB_EVAL_BLOCK, MPCB_EVAL_MINBLOCKS) k_ocp_eval(OcpArgs a) {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int inst = tid / NH, k = tid % NH;
     if (inst >= a.B) return;
@@ -89,7 +97,7 @@ __global__ void k_ocp_output(OcpArgs a, double* f, int* status, int* iters) {
 }
 
 // stage derivatives alone (mpcb_stage_derivs)
-__global__ void __launch_bounds__(128) k_stage_derivs(int B, const double* par, const double* w, const double* lam,
+__global__ void __launch_bounds__(MPCB_EVAL_BLOCK, MPCB_EVAL_MINBLOCKS) k_stage_derivs(int B, const double* par, const double* w, const double* lam,
                                                       double* A, double* Bm, double* c, double* H) {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int inst = tid / NH, k = tid % NH;
@@ -354,7 +362,7 @@ int mpcb_ocp(mpcb_handle_t h, const double* par, double* w, double* f, int* stat
     const int check_every = 2;
     while (ticks < max_ticks) {
         for (int c = 0; c < check_every; ++c) {
-            { Prof p(h, s, KC_OCP_EVAL); k_ocp_eval<<<nblk(nst, bs), bs, 0, s>>>(a); }
+            { Prof p(h, s, KC_OCP_EVAL); k_ocp_eval<<<nblk(nst, MPCB_EVAL_BLOCK), MPCB_EVAL_BLOCK, 0, s>>>(a); }
             { Prof p(h, s, KC_OCP_KKT); k_ocp_kkt<<<nblk((long)h->B * 32, 32 * KKT_WARPS), 32 * KKT_WARPS, 0, s>>>(a); }
             { Prof p(h, s, KC_OCP_TRIAL); k_ocp_trial<<<nblk(nst, bs), bs, 0, s>>>(a); }
             if (c == check_every - 1) CK(cudaMemsetAsync(h->n_active, 0, sizeof(int), s));
@@ -385,7 +393,7 @@ int mpcb_ocp(mpcb_handle_t h, const double* par, double* w, double* f, int* stat
 int mpcb_stage_derivs(mpcb_handle_t h, const double* par, const double* w, const double* lam,
                       double* A, double* Bm, double* c, double* H, void* stream) {
 #if MPCB_HAS_OCP
-    { Prof p(h, (cudaStream_t)stream, KC_OTHER); k_stage_derivs<<<nblk((long)h->B * NH, 128), 128, 0, (cudaStream_t)stream>>>(h->B, par, w, lam, A, Bm, c, H); }
+    { Prof p(h, (cudaStream_t)stream, KC_OTHER); k_stage_derivs<<<nblk((long)h->B * NH, MPCB_EVAL_BLOCK), MPCB_EVAL_BLOCK, 0, (cudaStream_t)stream>>>(h->B, par, w, lam, A, Bm, c, H); }
     CK(cudaGetLastError());
     h->last_launches = 1;
     return 0;

@@ -766,7 +766,10 @@ MPCB_HD void ocp_accept(OcpInst& I, const OcpShared& S) {
         const bool give_up = !(an >= amin * (1.0 - 1e-12)) || an <= 1e-16;
         if (lane == 0) { st.alpha = an; st.ls_iter += 1; }
         W_SYNC();
-        if (give_up) ocp_finish(I, S, -2);                      // no restoration phase
+        // No restoration phase.  IPOPT would now minimise the constraint violation; when that cannot be reduced it
+        // returns Infeasible_Problem_Detected (the status the reference loop acts on), so a failed line search away
+        // from feasibility (violation above constr_viol_tol = 1e-4) is reported as 2, otherwise Restoration_Failed.
+        if (give_up) ocp_finish(I, S, theta > 1e-4 ? 2 : -2);
         return;
     }
     // ---- take the step; bound multipliers with their own step size, then the kappa_sigma safeguard

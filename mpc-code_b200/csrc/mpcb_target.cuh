@@ -301,7 +301,7 @@ MPCB_HD void tgt_solve(const double* par, double* w, double* fout, int* status_o
             if (accepted) break;
             alpha *= 0.5;
         }
-        if (!accepted) { status = -2; break; }
+        if (!accepted) { status = theta > 1e-4 ? 2 : -2; break; }   // see ocp_accept: no restoration phase
         if (!ftype && nfilt < MPCB_MAXFILT) { filt[2 * nfilt] = (1.0 - 1e-5) * theta; filt[2 * nfilt + 1] = phi - 1e-8 * theta; nfilt++; }
         for (int j = 0; j < NWS; ++j) {
             w[j] = wt[j];

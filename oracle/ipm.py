@@ -17,7 +17,9 @@ reference and cannot be installed here, so this follows its published algorithm
   consecutive iterations at 1e-6;
 * filter line search (gamma_theta 1e-5, gamma_phi 1e-8, eta_phi 1e-8, s_theta 1.1, s_phi 2.3,
   delta 1) with backtracking by 1/2; no second-order correction, no watchdog and no restoration
-  phase (a failed line search ends with ``Restoration_Failed``);
+  phase: a failed line search ends with ``Infeasible_Problem_Detected`` when the constraint
+  violation is above ``constr_viol_tol`` (what IPOPT's restoration reports when it cannot reduce
+  it) and with ``Restoration_Failed`` otherwise;
 * inertia correction of the augmented system by the delta_w ladder (1e-4 first, x100 / x8 up,
   /3 down) using a dense symmetric-indefinite factorisation (LAPACK ``dsytrf``) for the inertia.
 
@@ -360,7 +362,10 @@ def solve_nlp(n: int, m: int, fun: Callable, x0, xL, xU, gL, gU, opts: Optional[
             print("it %3d mu %.1e E0 %.2e theta %.3e phi %.8e gphid %.2e amax %.2e az %.2e alpha %.2e dw %.1e %s nfilt %d a_min %.1e"
                   % (it, mu, E0, theta, phi, gphi_d, alpha_max, alpha_z, alpha, delta_w, "acc" if accepted else "REJ", len(filt), a_min))
         if not accepted:
-            status = -2
+            # IPOPT would enter its restoration phase here.  It is not restated; what it reports when the violation
+            # cannot be reduced - Infeasible_Problem_Detected - is returned whenever the line search fails away from
+            # feasibility (violation above constr_viol_tol), otherwise Restoration_Failed.
+            status = 2 if theta > o.constr_viol_tol else -2
             break
         if not ftype:
             filt.append(((1 - o.gamma_theta) * theta, phi - o.gamma_phi * theta))
