@@ -40,7 +40,11 @@ def source_digest(header_text: str) -> str:
 
 
 def build_library(name: str, prob, ss_spec, ocp_spec, verbose: bool = False, extra_flags=()) -> dict:
-    """Generate the header and compile; returns ``{"so": path, "header": path, "gen": generate_header(...)}``."""
+    """Generate the header and compile; returns ``{"so": path, "header": path, "gen": generate_header(...)}``.
+
+    ``MPCB_EXTRA_FLAGS`` (environment, space separated) appends nvcc flags - used by the tuning scripts to try
+    kernel mappings (e.g. ``-DMPCB_KKT_LANES=32``)."""
+    extra_flags = tuple(extra_flags) + tuple(os.environ.get("MPCB_EXTRA_FLAGS", "").split())
     gen = generate_header(prob, ss_spec, ocp_spec)
     digest = source_digest(gen["text"] + " ".join(extra_flags))
     work = os.path.join(BUILD_DIR, "%s_%s" % (name, digest))

@@ -19,7 +19,7 @@ enum { KC_OCP_INIT = 0, KC_OCP_EVAL = 1, KC_OCP_KKT = 2, KC_OCP_TRIAL = 3, KC_OC
 #define MPCB_EVAL_BLOCK 128
 #endif
 #ifndef MPCB_EVAL_MINBLOCKS
-#define MPCB_EVAL_MINBLOCKS 2
+#define MPCB_EVAL_MINBLOCKS 3
 #endif
 
 #ifndef MPCB_FLOPS_TABLE
@@ -59,8 +59,12 @@ __global__ void __launch_bounds__(MPCB_EVAL_BLOCK, MPCB_EVAL_MINBLOCKS) k_ocp_ev
     ocp_eval_stage(I, a.S, k);
 }
 
-// one warp per instance (lanes over stages / matrix entries; per-warp scratch in shared memory)
+// KKT step: one thread per instance (small stage blocks, MPCB_KKT_LANES == 1) or one warp per instance with
+// per-warp scratch in shared memory (MPCB_KKT_LANES == 32)
+#ifndef KKT_WARPS
 #define KKT_WARPS 4
+#endif
+#if MPCB_KKT_LANES == 32
 __global__ void __launch_bounds__(32 * KKT_WARPS) k_ocp_kkt(OcpArgs a) {
     __shared__ double scratch[KKT_WARPS][KktScratch::total];
     const int inst = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -69,6 +73,18 @@ __global__ void __launch_bounds__(32 * KKT_WARPS) k_ocp_kkt(OcpArgs a) {
     OcpInst I = ocp_view(a, inst);
     ocp_kkt(I, a.S, scratch[threadIdx.x >> 5]);
 }
+#define KKT_GRID(B) nblk((long)(B) * 32, 32 * KKT_WARPS), 32 * KKT_WARPS
+#else
+__global__ void __launch_bounds__(32) k_ocp_kkt(OcpArgs a) {
+    const int inst = blockIdx.x * blockDim.x + threadIdx.x;
+    if (inst >= a.B) return;
+    if (a.st[inst].state != ST_EVAL) return;
+    double scratch[KktScratch::total];
+    OcpInst I = ocp_view(a, inst);
+    ocp_kkt(I, a.S, scratch);
+}
+#define KKT_GRID(B) nblk((long)(B), 32), 32
+#endif
 
 __global__ void __launch_bounds__(128) k_ocp_trial(OcpArgs a) {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -363,7 +379,7 @@ int mpcb_ocp(mpcb_handle_t h, const double* par, double* w, double* f, int* stat
     while (ticks < max_ticks) {
         for (int c = 0; c < check_every; ++c) {
             { Prof p(h, s, KC_OCP_EVAL); k_ocp_eval<<<nblk(nst, MPCB_EVAL_BLOCK), MPCB_EVAL_BLOCK, 0, s>>>(a); }
-            { Prof p(h, s, KC_OCP_KKT); k_ocp_kkt<<<nblk((long)h->B * 32, 32 * KKT_WARPS), 32 * KKT_WARPS, 0, s>>>(a); }
+            { Prof p(h, s, KC_OCP_KKT); k_ocp_kkt<<<KKT_GRID(h->B), 0, s>>>(a); }
             { Prof p(h, s, KC_OCP_TRIAL); k_ocp_trial<<<nblk(nst, bs), bs, 0, s>>>(a); }
             if (c == check_every - 1) CK(cudaMemsetAsync(h->n_active, 0, sizeof(int), s));
             { Prof p(h, s, KC_OCP_ACCEPT); k_ocp_accept<<<nblk((long)h->B * 32, 32 * KKT_WARPS), 32 * KKT_WARPS, 0, s>>>(a, h->n_active); }

@@ -40,14 +40,57 @@ struct InstState {
 struct OcpInst {
     double* w; const double* par;
     double *lam, *lamn, *s, *ds, *ym, *dym, *zL, *zU, *vL, *vU, *dw;
-    double *A, *Bm, *c, *H, *gl, *HN, *gN, *G, *gv;
-    double *Pm, *pv, *Kf, *kf, *part, *partt;
+    double *rec, *trec, *frec, *partt;
     InstState* st;
 };
 struct OcpShared { const double *lbx, *ubx, *lbg, *ubg; IpmOpts o; };
 
-// ---- sizes of the per-instance workspace (doubles) -------------------------------------------
+// ---- per-stage records ------------------------------------------------------------------------
+// k_ocp_eval condenses everything the Newton step needs from stage k into ONE contiguous record, so that the
+// sequential sweeps of the KKT step stream memory instead of gathering from a dozen arrays:
 #define NGS (NG > 0 ? NG : 1)
+#define R_AB   0                          // NX*NZ  [A_k | B_k], column-major
+#define R_C    (R_AB + NX * NZ)           // NX     defect  Fx(x_k,u_k) - x_{k+1}
+#define R_M    (R_C + NX)                 // NZ*NZ  H_k + diag(zL/dL + zU/dU) + G' Sigma_s G   (delta_w = 0)
+#define R_GL   (R_M + NZ * NZ)            // NZ     gradient of the stage cost
+#define R_IL   (R_GL + NZ)                // NZ     1 / (v - lo)  (0: no lower bound / fixed x_0)
+#define R_IU   (R_IL + NZ)                // NZ     1 / (hi - v)
+#define R_ZL   (R_IU + NZ)                // NZ
+#define R_ZU   (R_ZL + NZ)                // NZ
+#define R_QL   (R_ZU + NZ)                // NZ     (1/(v-lo)) / zL   (0: no bound) - keeps the step-size rules division free
+#define R_QU   (R_QL + NZ)                // NZ     (1/(hi-v)) / zU
+#define R_G    (R_QU + NZ)                // NG*NZ  Jacobian of the range rows (column-major NG x NZ)
+#define R_SG   (R_G + NGS * NZ)           // NG     Sigma_s = vL/(s-lo) + vU/(hi-s)
+#define R_ISL  (R_SG + NGS)               // NG     1 / (s - lo)
+#define R_ISU  (R_ISL + NGS)              // NG     1 / (hi - s)
+#define R_VL   (R_ISU + NGS)              // NG
+#define R_VU   (R_VL + NGS)               // NG
+#define R_QSL  (R_VU + NGS)               // NG     (1/(s-lo)) / vL
+#define R_QSU  (R_QSL + NGS)              // NG     (1/(hi-s)) / vU
+#define R_RG   (R_QSU + NGS)              // NG     g - s
+#define R_YM   (R_RG + NGS)               // NG     multiplier of the range row
+#define R_GV   (R_YM + NGS)               // NG     g
+#define R_PART (R_GV + NGS)               // 10: cost, theta, dual_max, prim_max, ysum, zsum, nb, pmin, pmax, sum log(slack)
+#define NPART  10
+#define REC_SZ ((R_PART + NPART + 1) / 2 * 2)
+// terminal record (x_N)
+#define T_H    0                          // NX*NX  Hessian of the terminal cost
+#define T_GN   (NX * NX)                  // NX     its gradient
+#define T_IL   (T_GN + NX)
+#define T_IU   (T_IL + NX)
+#define T_ZL   (T_IU + NX)
+#define T_ZU   (T_ZL + NX)
+#define T_QL   (T_ZU + NX)
+#define T_QU   (T_QL + NX)
+#define T_PART (T_QU + NX)                // 10: V, 0, dual_max, 0, 0, zsum, nb, pmin, pmax, sum log(slack)
+#define TREC_SZ ((T_PART + NPART + 1) / 2 * 2)
+// forward records written by the Riccati sweep
+#define FREC_K   0
+#define FREC_KF  (NU * NX)
+#define FREC_P   (FREC_KF + NU)
+#define FREC_PV  (FREC_P + NX * NX)
+#define FREC_SZ  ((FREC_PV + NX + 1) / 2 * 2)
+
 struct OcpLayout {
     static constexpr int lam = 0;
     static constexpr int lamn = lam + NH * NX;
@@ -60,22 +103,11 @@ struct OcpLayout {
     static constexpr int zL = vU + NH * NGS;
     static constexpr int zU = zL + NW;
     static constexpr int dw = zU + NW;
-    static constexpr int A = dw + NW;
-    static constexpr int Bm = A + NH * NX * NX;
-    static constexpr int c = Bm + NH * NX * NU;
-    static constexpr int H = c + NH * NX;
-    static constexpr int gl = H + NH * NZP;
-    static constexpr int HN = gl + NH * NZ;
-    static constexpr int gN = HN + NXP_;
-    static constexpr int G = gN + NX;
-    static constexpr int gv = G + NH * NGS * NZ;
-    static constexpr int Pm = gv + NH * NGS;
-    static constexpr int pv = Pm + (NH + 1) * NX * NX;
-    static constexpr int Kf = pv + (NH + 1) * NX;
-    static constexpr int kf = Kf + NH * NU * NX;
-    static constexpr int part = kf + NH * NU;
-    static constexpr int partt = part + (NH + 1) * 4;
-    static constexpr int total = partt + (NH + 1) * 4;
+    static constexpr int rec = (dw + NW + 1) / 2 * 2;
+    static constexpr int trec = rec + NH * REC_SZ;
+    static constexpr int frec = trec + TREC_SZ;
+    static constexpr int partt = frec + NH * FREC_SZ;
+    static constexpr int total = (partt + (NH + 1) * 4 + 1) / 2 * 2;
 };
 
 MPCB_HD OcpInst ocp_inst(double* ws, double* w, const double* par, InstState* st) {
@@ -84,10 +116,8 @@ MPCB_HD OcpInst ocp_inst(double* ws, double* w, const double* par, InstState* st
     I.lam = ws + OcpLayout::lam; I.lamn = ws + OcpLayout::lamn; I.s = ws + OcpLayout::s; I.ds = ws + OcpLayout::ds;
     I.ym = ws + OcpLayout::ym; I.dym = ws + OcpLayout::dym; I.vL = ws + OcpLayout::vL; I.vU = ws + OcpLayout::vU;
     I.zL = ws + OcpLayout::zL; I.zU = ws + OcpLayout::zU; I.dw = ws + OcpLayout::dw;
-    I.A = ws + OcpLayout::A; I.Bm = ws + OcpLayout::Bm; I.c = ws + OcpLayout::c; I.H = ws + OcpLayout::H;
-    I.gl = ws + OcpLayout::gl; I.HN = ws + OcpLayout::HN; I.gN = ws + OcpLayout::gN; I.G = ws + OcpLayout::G;
-    I.gv = ws + OcpLayout::gv; I.Pm = ws + OcpLayout::Pm; I.pv = ws + OcpLayout::pv; I.Kf = ws + OcpLayout::Kf;
-    I.kf = ws + OcpLayout::kf; I.part = ws + OcpLayout::part; I.partt = ws + OcpLayout::partt;
+    I.rec = ws + OcpLayout::rec; I.trec = ws + OcpLayout::trec; I.frec = ws + OcpLayout::frec;
+    I.partt = ws + OcpLayout::partt;
     return I;
 }
 
@@ -165,10 +195,23 @@ MPCB_HD void ocp_init_stage(OcpInst& I, const OcpShared& S, int k) {
 }
 
 // =============================================================================================
-// eval: derivatives of stage k at the current iterate (k = 0..NH-1; k = NH-1 also does the terminal)
+// eval: derivatives of stage k at the current iterate, condensed into the stage record
+// (k = 0..NH-1; k = NH-1 also writes the terminal record)
 // =============================================================================================
+MPCB_HD void bound_terms(double v, double lo, double hi, double zl, double zu, double rf, bool active,
+                         double* iL, double* iU, double* zL, double* zU, double* qL, double* qU, double* sig,
+                         double* zsum, double* nb, double* pmin, double* pmax, double* prod) {
+    *iL = *iU = *zL = *zU = *qL = *qU = 0.0;
+    if (!active) return;
+    if (fin(lo)) { const double d = v - rlo(lo, rf); const double id = 1.0 / d; *iL = id; *zL = zl; *qL = id / zl; *sig += zl * id;
+                   *zsum += zl; *nb += 1.0; *pmin = fmin(*pmin, d * zl); *pmax = fmax(*pmax, d * zl); *prod *= d; }
+    if (fin(hi)) { const double d = rhi(hi, rf) - v; const double id = 1.0 / d; *iU = id; *zU = zu; *qU = id / zu; *sig += zu * id;
+                   *zsum += zu; *nb += 1.0; *pmin = fmin(*pmin, d * zu); *pmax = fmax(*pmax, d * zu); *prod *= d; }
+}
+
 MPCB_HD void ocp_eval_stage(OcpInst& I, const OcpShared& S, int k) {
     const double* w = I.w;
+    const double rf = S.o.bound_relax;
     double x[NX], u[NU], lam[NX], d[ND + 1], px[NPX + 1], py[NPY + 1], t0;
 #pragma unroll
     for (int i = 0; i < NX; ++i) { x[i] = w[k * NZ + i]; lam[i] = I.lam[k * NX + i]; }
@@ -178,13 +221,39 @@ MPCB_HD void ocp_eval_stage(OcpInst& I, const OcpShared& S, int k) {
     double xn[NX], A[NX * NX], Bm[NX * NU], Hp[NZP], l, g[NZ];
     ocp_cost_d(x, u, I.par, px, py, &l, g, Hp);          // Hp <- cost Hessian, then accumulate the rest
     dyn_full(x, u, d, px, t0, lam, xn, A, Bm, Hp);
-    double th = 0.0;
+    double* r = I.rec + k * REC_SZ;
+    double th = 0.0, prim = 0.0, ysum = 0.0, zsum = 0.0, nb = 0.0, pmin = 1e300, pmax = -1e300;
+    double prod = 1.0;     // product of all slacks-to-bounds of the stage: one log instead of one per bound
 #pragma unroll
     for (int i = 0; i < NX; ++i) {
         const double ci = xn[i] - w[(k + 1) * NZ + i];
-        I.c[k * NX + i] = ci;
-        th += fabs(ci);
+        r[R_C + i] = ci;
+        th += fabs(ci); prim = fmax(prim, fabs(ci)); ysum += fabs(lam[i]);
     }
+    // dual residual of the stage variables, started with the cost gradient and the dynamics multipliers
+    double res[NZ], dg[NZ];
+#pragma unroll
+    for (int j = 0; j < NZ; ++j) {
+        double a = g[j];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) a += ((j < NX) ? A[i + NX * j] : Bm[i + NX * (j - NX)]) * lam[i];
+        if (j < NX && k > 0) a -= I.lam[(k - 1) * NX + j];
+        res[j] = a; dg[j] = 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < NZ; ++j) {
+        const int wi = k * NZ + j;
+        const bool active = !(k == 0 && j < NX);          // x_0 is fixed
+        double iL, iU, zL, zU, qL, qU;
+        bound_terms(w[wi], S.lbx[wi], S.ubx[wi], I.zL[wi], I.zU[wi], rf, active, &iL, &iU, &zL, &zU, &qL, &qU, &dg[j], &zsum, &nb, &pmin, &pmax, &prod);
+        r[R_IL + j] = iL; r[R_IU + j] = iU; r[R_ZL + j] = zL; r[R_ZU + j] = zU; r[R_QL + j] = qL; r[R_QU + j] = qU; r[R_GL + j] = g[j];
+        res[j] += zU - zL;
+    }
+    double M[NZ * NZ], dual_s = 0.0;
+#pragma unroll
+    for (int j = 0; j < NZ; ++j)
+#pragma unroll
+        for (int i = 0; i < NZ; ++i) M[i + NZ * j] = Hp[tri(i, j)] + (i == j ? dg[j] : 0.0);
 #if NG > 0
     {
         double Y[NG], JY[NG * NZ], HY[NZP], mult[NG];
@@ -193,49 +262,83 @@ MPCB_HD void ocp_eval_stage(OcpInst& I, const OcpShared& S, int k) {
         ocp_out_d(x, u, I.par, py, mult, Y, JY, HY);
 #if !MPCB_OUT_LINEAR
 #pragma unroll
-        for (int i = 0; i < NZP; ++i) Hp[i] += HY[i];
+        for (int j = 0; j < NZ; ++j)
+#pragma unroll
+            for (int i = 0; i < NZ; ++i) M[i + NZ * j] += HY[tri(i, j)];
 #endif
 #pragma unroll
-        for (int i = 0; i < NG; ++i) { I.gv[k * NG + i] = Y[i]; th += fabs(Y[i] - I.s[k * NG + i]); }
+        for (int q = 0; q < NG; ++q) {
+            const int gi = k * NG + q;
+            const double sv = I.s[gi], lo = S.lbg[gi], hi = S.ubg[gi];
+            double isl, isu, vl, vu, qsl, qsu, sig = 0.0;
+            bound_terms(sv, lo, hi, I.vL[gi], I.vU[gi], rf, true, &isl, &isu, &vl, &vu, &qsl, &qsu, &sig, &zsum, &nb, &pmin, &pmax, &prod);
+            const double rg = Y[q] - sv;
+            r[R_SG + q] = sig; r[R_ISL + q] = isl; r[R_ISU + q] = isu; r[R_VL + q] = vl; r[R_VU + q] = vu;
+            r[R_QSL + q] = qsl; r[R_QSU + q] = qsu;
+            r[R_RG + q] = rg; r[R_YM + q] = mult[q]; r[R_GV + q] = Y[q];
+            th += fabs(rg); prim = fmax(prim, fabs(rg)); ysum += fabs(mult[q]);
+            dual_s = fmax(dual_s, fabs(-mult[q] - vl + vu));   // dual residual of the slack
 #pragma unroll
-        for (int i = 0; i < NG * NZ; ++i) I.G[k * NG * NZ + i] = JY[i];
+            for (int j = 0; j < NZ; ++j) {
+                r[R_G + q + NG * j] = JY[q + NG * j];
+                res[j] += JY[q + NG * j] * mult[q];
+#pragma unroll
+                for (int i = 0; i < NZ; ++i) M[i + NZ * j] += JY[q + NG * i] * sig * JY[q + NG * j];
+            }
+        }
     }
 #endif
+    double dual = dual_s;
 #pragma unroll
-    for (int i = 0; i < NX * NX; ++i) I.A[k * NX * NX + i] = A[i];
+    for (int j = 0; j < NZ; ++j) if (!(k == 0 && j < NX)) dual = fmax(dual, fabs(res[j]));
 #pragma unroll
-    for (int i = 0; i < NX * NU; ++i) I.Bm[k * NX * NU + i] = Bm[i];
+    for (int i = 0; i < NX * NX; ++i) r[R_AB + i] = A[i];
 #pragma unroll
-    for (int i = 0; i < NZP; ++i) I.H[k * NZP + i] = Hp[i];
+    for (int i = 0; i < NX * NU; ++i) r[R_AB + NX * NX + i] = Bm[i];
 #pragma unroll
-    for (int i = 0; i < NZ; ++i) I.gl[k * NZ + i] = g[i];
-    I.part[k * 4 + 0] = l;
-    I.part[k * 4 + 1] = th;
+    for (int i = 0; i < NZ * NZ; ++i) r[R_M + i] = M[i];
+    r[R_PART + 0] = l; r[R_PART + 1] = th; r[R_PART + 2] = dual; r[R_PART + 3] = prim; r[R_PART + 4] = ysum;
+    r[R_PART + 5] = zsum; r[R_PART + 6] = nb; r[R_PART + 7] = pmin; r[R_PART + 8] = pmax; r[R_PART + 9] = log(prod);
     if (k == NH - 1) {
         double V, gN[NX], HN[NXP_ + 1];
+        double* t = I.trec;
         ocp_term_d(w + NH * NZ, I.par, &V, gN, HN);
+        double dualN = 0.0, zs = 0.0, nbn = 0.0, pmn = 1e300, pmx = -1e300, prodN = 1.0;
 #pragma unroll
-        for (int i = 0; i < NX; ++i) I.gN[i] = gN[i];
+        for (int j = 0; j < NX; ++j) {
+            const int wi = NH * NZ + j;
+            double iL, iU, zL, zU, qL, qU, sig = 0.0;
+            bound_terms(w[wi], S.lbx[wi], S.ubx[wi], I.zL[wi], I.zU[wi], rf, true, &iL, &iU, &zL, &zU, &qL, &qU, &sig, &zs, &nbn, &pmn, &pmx, &prodN);
+            t[T_IL + j] = iL; t[T_IU + j] = iU; t[T_ZL + j] = zL; t[T_ZU + j] = zU; t[T_QL + j] = qL; t[T_QU + j] = qU; t[T_GN + j] = gN[j];
+            dualN = fmax(dualN, fabs(gN[j] - lam[j] + zU - zL));          // lam = lam_N for k = NH-1
 #pragma unroll
-        for (int i = 0; i < NXP_; ++i) I.HN[i] = HN[i];
-        I.part[NH * 4 + 0] = V;
-        I.part[NH * 4 + 1] = 0.0;
+            for (int i = 0; i < NX; ++i) t[T_H + i + NX * j] = HN[tri(i, j)];
+        }
+        t[T_PART + 0] = V; t[T_PART + 1] = 0.0; t[T_PART + 2] = dualN; t[T_PART + 3] = 0.0; t[T_PART + 4] = 0.0;
+        t[T_PART + 5] = zs; t[T_PART + 6] = nbn; t[T_PART + 7] = pmn; t[T_PART + 8] = pmx; t[T_PART + 9] = log(prodN);
     }
 }
 
 // =============================================================================================
-// Lane-generic helpers.  ocp_kkt / ocp_accept are written once and run either by the 32 lanes of a
-// warp (device: one warp per instance, lanes strided over stages / matrix entries, reductions by
-// shuffle, small per-warp scratch in shared memory) or by a single "lane" on the host (tests).
+// Lane-generic helpers.  ocp_kkt / ocp_accept are written once and run either by MPCB_KKT_LANES = 32 lanes
+// of a warp (lanes strided over matrix entries, reductions by shuffle, per-warp scratch in shared memory:
+// the mapping for large stage blocks), by one device thread per instance (MPCB_KKT_LANES = 1: everything in
+// registers, records streamed with 128-bit loads - the mapping for small systems such as Ex_NMPC), or by a
+// single host "lane" (tests).
 // =============================================================================================
-#ifdef __CUDA_ARCH__
+// Measured on B200 at 4 096 instances (profiles/r01_variants.txt): one warp per instance is faster than one thread per
+// instance (the latter has 5x fewer instructions but only 128 warps to hide latency with); the thread mapping is the
+// one to pick for very large batches and is kept selectable at build time (-DMPCB_KKT_LANES=1).
+#ifndef MPCB_KKT_LANES
+#  define MPCB_KKT_LANES 32
+#endif
+#if defined(__CUDA_ARCH__) && (MPCB_KKT_LANES == 32)
 #  define LANE_ID   ((int)(threadIdx.x & 31))
 #  define N_LANES   32
 #  define W_SYNC()  __syncwarp()
 #  define W_SUM(v)  warp_sum(v)
 #  define W_MAX(v)  warp_max(v)
 #  define W_MIN(v)  warp_min(v)
-#  define W_ISUM(v) warp_sum_int(v)
 #else
 #  define LANE_ID   0
 #  define N_LANES   1
@@ -243,263 +346,171 @@ MPCB_HD void ocp_eval_stage(OcpInst& I, const OcpShared& S, int k) {
 #  define W_SUM(v)  (v)
 #  define W_MAX(v)  (v)
 #  define W_MIN(v)  (v)
-#  define W_ISUM(v) (v)
 #endif
 
-// per-warp scratch (doubles)
+// scratch (doubles): shared memory per warp with 32 lanes, thread-local (registers) with one lane
 struct KktScratch {
-    static constexpr int P = 0;                       // NX x NX   cost-to-go Hessian of the next stage
+    static constexpr int R = 0;                                     // staged record (32-lane mapping only)
+    static constexpr int P = R + (MPCB_KKT_LANES == 32 ? REC_SZ : 0);   // NX x NX  cost-to-go Hessian of the next stage
     static constexpr int p = P + NX * NX;             // NX
-    static constexpr int M = p + NX;                  // NZ x NZ   condensed stage Hessian
+    static constexpr int M = p + NX;                  // NZ x NZ  condensed stage Hessian
     static constexpr int q = M + NZ * NZ;             // NZ
-    static constexpr int T = q + NZ;                  // NX x NZ   P [A B]
-    static constexpr int f = T + NX * NZ;             // NX        P c + p
-    static constexpr int AB = f + NX;                 // NX x NZ   [A B]
-    static constexpr int K = AB + NX * NZ;            // NU x NX
+    static constexpr int T = q + NZ;                  // NX x NZ  P [A B]
+    static constexpr int f = T + NX * NZ;             // NX       P c + p
+    static constexpr int K = f + NX;                  // NU x NX
     static constexpr int kk = K + NU * NX;            // NU
-    static constexpr int sg = kk + NU;                // NGS       slack barrier curvature
-    static constexpr int cf = sg + NGS;               // NGS       slack gradient coefficient
+    static constexpr int cf = kk + NU;                // NGS      slack gradient coefficient
     static constexpr int dx = cf + NGS;               // NX
     static constexpr int du = dx + NX;                // NU
     static constexpr int dxn = du + NU;               // NX
     static constexpr int total = dxn + NX;
 };
 
-// complementarity error  max |slack * z - mu|  over all bounds
-MPCB_HD double ocp_compl(const OcpInst& I, const OcpShared& S, double mu) {
-    const double rf = S.o.bound_relax;
-    double e = 0.0;
-    for (int i = NX + LANE_ID; i < NW; i += N_LANES) {
-        const double lo = S.lbx[i], hi = S.ubx[i];
-        if (fin(lo)) e = fmax(e, fabs((I.w[i] - rlo(lo, rf)) * I.zL[i] - mu));
-        if (fin(hi)) e = fmax(e, fabs((rhi(hi, rf) - I.w[i]) * I.zU[i] - mu));
-    }
-#if NG > 0
-    for (int i = LANE_ID; i < NH * NG; i += N_LANES) {
-        const double lo = S.lbg[i], hi = S.ubg[i];
-        if (fin(lo)) e = fmax(e, fabs((I.s[i] - rlo(lo, rf)) * I.vL[i] - mu));
-        if (fin(hi)) e = fmax(e, fabs((rhi(hi, rf) - I.s[i]) * I.vU[i] - mu));
-    }
+// Make the record of a stage readable by all lanes: staged through shared memory for a warp, read in place
+// (global memory, contiguous 128-bit loads) for a single lane.
+MPCB_HD const double* stage_record(const double* rk, double* sm, int n) {
+#if defined(__CUDA_ARCH__) && (MPCB_KKT_LANES == 32)
+    double* R = sm + KktScratch::R;
+    W_SYNC();
+    for (int e = LANE_ID; e < n; e += N_LANES) R[e] = rk[e];
+    W_SYNC();
+    return R;
+#else
+    (void)sm; (void)n;
+    return rk;
 #endif
-    return W_MAX(e);
 }
 
-struct KktErr { double dual, prim, sd, sc; };
-
-// dual / primal infeasibility and the IPOPT scaling factors s_d, s_c (s_max = 100)
-MPCB_HD KktErr ocp_errors(const OcpInst& I, const OcpShared& S) {
-    double dual = 0.0, prim = 0.0, ysum = 0.0, zsum = 0.0;
-    int nb = 0;
-    for (int k = LANE_ID; k <= NH; k += N_LANES) {
-        if (k == NH) {                                            // terminal state
-            for (int j = 0; j < NX; ++j) {
-                const int wi = NH * NZ + j;
-                const double r = I.gN[j] - I.lam[(NH - 1) * NX + j] + I.zU[wi] - I.zL[wi];
-                dual = fmax(dual, fabs(r));
-                zsum += I.zL[wi] + I.zU[wi];
-                nb += (fin(S.lbx[wi]) ? 1 : 0) + (fin(S.ubx[wi]) ? 1 : 0);
-            }
-            continue;
-        }
-        const double* A = I.A + k * NX * NX; const double* Bm = I.Bm + k * NX * NU;
-        const double* lamn = I.lam + k * NX;                  // lam_{k+1}
-        for (int j = 0; j < NZ; ++j) {
-            if (k == 0 && j < NX) continue;                   // x0 is fixed
-            const int wi = k * NZ + j;
-            double r = I.gl[k * NZ + j];
-            const double* col = (j < NX) ? (A + NX * j) : (Bm + NX * (j - NX));
-            for (int i = 0; i < NX; ++i) r += col[i] * lamn[i];
-            if (j < NX) r -= I.lam[(k - 1) * NX + j];         // -lam_k
-#if NG > 0
-            for (int i = 0; i < NG; ++i) r += I.G[k * NG * NZ + i + NG * j] * I.ym[k * NG + i];
-#endif
-            r += I.zU[wi] - I.zL[wi];
-            dual = fmax(dual, fabs(r));
-            zsum += I.zL[wi] + I.zU[wi];
-            nb += (fin(S.lbx[wi]) ? 1 : 0) + (fin(S.ubx[wi]) ? 1 : 0);
-        }
-        for (int i = 0; i < NX; ++i) { prim = fmax(prim, fabs(I.c[k * NX + i])); ysum += fabs(lamn[i]); }
-#if NG > 0
-        for (int i = 0; i < NG; ++i) {
-            const int gi = k * NG + i;
-            prim = fmax(prim, fabs(I.gv[gi] - I.s[gi]));
-            dual = fmax(dual, fabs(-I.ym[gi] - I.vL[gi] + I.vU[gi]));
-            ysum += fabs(I.ym[gi]);
-            zsum += I.vL[gi] + I.vU[gi];
-            nb += (fin(S.lbg[gi]) ? 1 : 0) + (fin(S.ubg[gi]) ? 1 : 0);
-        }
-#endif
-    }
-    dual = W_MAX(dual); prim = W_MAX(prim); ysum = W_SUM(ysum); zsum = W_SUM(zsum); nb = W_ISUM(nb);
-    const double smax = 100.0;
-    const int mc = NH * NX + NH * NG;
-    KktErr e;
-    e.dual = dual; e.prim = prim;
-    e.sd = fmax(smax, (ysum + zsum) / (double)(mc + nb > 0 ? mc + nb : 1)) / smax;
-    e.sc = fmax(smax, zsum / (double)(nb > 0 ? nb : 1)) / smax;
-    return e;
-}
-
-// Riccati backward sweep with regularisation dw on every primal variable.  Returns false when some
-// R_k + B_k' P_{k+1} B_k is not positive definite (wrong inertia).  `sm` is the per-warp scratch.
-MPCB_HD bool ocp_riccati(OcpInst& I, const OcpShared& S, double mu, double dwreg, double* sm) {
-    const double rf = S.o.bound_relax;
+// Riccati backward sweep with regularisation dw on every primal variable (and slack).  Returns false when
+// some R_k + B_k' P_{k+1} B_k is not positive definite (wrong inertia).
+MPCB_HD bool ocp_riccati(OcpInst& I, double mu, double dwreg, double* sm) {
     const int lane = LANE_ID;
     double* P = sm + KktScratch::P; double* p = sm + KktScratch::p; double* M = sm + KktScratch::M;
     double* q = sm + KktScratch::q; double* T = sm + KktScratch::T; double* f = sm + KktScratch::f;
-    double* AB = sm + KktScratch::AB; double* Kk = sm + KktScratch::K; double* kk = sm + KktScratch::kk;
-    double* sg = sm + KktScratch::sg; double* cf = sm + KktScratch::cf;
-    // terminal stage
-    for (int e = lane; e < NX * NX; e += N_LANES) {
-        const int i = e % NX, j = e / NX;
-        double v = I.HN[tri(i, j)];
-        if (i == j) {
-            const int wi = NH * NZ + i;
-            const double lo = S.lbx[wi], hi = S.ubx[wi];
-            v += dwreg;
-            if (fin(lo)) v += I.zL[wi] / (I.w[wi] - rlo(lo, rf));
-            if (fin(hi)) v += I.zU[wi] / (rhi(hi, rf) - I.w[wi]);
+    double* Kk = sm + KktScratch::K; double* kk = sm + KktScratch::kk; double* cf = sm + KktScratch::cf;
+    // ---- terminal stage
+    {
+        const double* t = I.trec;
+        for (int e = lane; e < NX * NX; e += N_LANES) {
+            const int i = e % NX, j = e / NX;
+            double v = t[T_H + e];
+            if (i == j) v += dwreg + t[T_ZL + i] * t[T_IL + i] + t[T_ZU + i] * t[T_IU + i];
+            P[e] = v;
         }
-        P[e] = v;
-        I.Pm[NH * NX * NX + e] = v;
-    }
-    for (int i = lane; i < NX; i += N_LANES) {
-        const int wi = NH * NZ + i;
-        const double lo = S.lbx[wi], hi = S.ubx[wi];
-        double qv = I.gN[i];
-        if (fin(lo)) qv -= mu / (I.w[wi] - rlo(lo, rf));
-        if (fin(hi)) qv += mu / (rhi(hi, rf) - I.w[wi]);
-        p[i] = qv;
-        I.pv[NH * NX + i] = qv;
+        for (int i = lane; i < NX; i += N_LANES) p[i] = t[T_GN + i] - mu * t[T_IL + i] + mu * t[T_IU + i];
     }
     W_SYNC();
     for (int k = NH - 1; k >= 0; --k) {
-        // ---- (a) load [A B]; slack barrier terms of the range rows
-        for (int e = lane; e < NX * NZ; e += N_LANES)
-            AB[e] = (e < NX * NX) ? I.A[k * NX * NX + e] : I.Bm[k * NX * NU + (e - NX * NX)];
+        const double* R = stage_record(I.rec + k * REC_SZ, sm, R_PART);
+        double* fk = I.frec + k * FREC_SZ;
+        // (a) P_{k+1}, p_{k+1} go to the forward record; slack coefficients
+        for (int e = lane; e < NX * NX; e += N_LANES) fk[FREC_P + e] = P[e];
+        for (int e = lane; e < NX; e += N_LANES) fk[FREC_PV + e] = p[e];
 #if NG > 0
-        for (int r = lane; r < NG; r += N_LANES) {
-            const int gi = k * NG + r;
-            const double lo = S.lbg[gi], hi = S.ubg[gi];
-            double sig = dwreg, b = 0.0;
-            if (fin(lo)) { const double dl = I.s[gi] - rlo(lo, rf); sig += I.vL[gi] / dl; b -= mu / dl; }
-            if (fin(hi)) { const double du = rhi(hi, rf) - I.s[gi]; sig += I.vU[gi] / du; b += mu / du; }
-            sg[r] = sig;
-            cf[r] = sig * (I.gv[gi] - I.s[gi]) + b;
-        }
+        for (int r = lane; r < NG; r += N_LANES)
+            cf[r] = (R[R_SG + r] + dwreg) * R[R_RG + r] - mu * R[R_ISL + r] + mu * R[R_ISU + r];
 #endif
-        W_SYNC();
-        // ---- (b) f = P c + p ;  T = P [A B]
+        // (b) f = P c + p ;  T = P [A B]
         for (int i = lane; i < NX; i += N_LANES) {
             double a = p[i];
-            for (int j = 0; j < NX; ++j) a += P[i + NX * j] * I.c[k * NX + j];
+            for (int j = 0; j < NX; ++j) a += P[i + NX * j] * R[R_C + j];
             f[i] = a;
         }
         for (int e = lane; e < NX * NZ; e += N_LANES) {
             const int i = e % NX, j = e / NX;
             double a = 0.0;
-            for (int l = 0; l < NX; ++l) a += P[i + NX * l] * AB[l + NX * j];
+            for (int l = 0; l < NX; ++l) a += P[i + NX * l] * R[R_AB + l + NX * j];
             T[e] = a;
         }
         W_SYNC();
-        // ---- (c) condensed stage Hessian M and gradient q, plus [A B]' P [A B] and [A B]' f
+        // (c) M = M0 + dw (I + G'G) + [A B]' P [A B] ;  q = grad - mu/dL + mu/dU + G' cf + [A B]' f
         for (int e = lane; e < NZ * NZ; e += N_LANES) {
             const int i = e % NZ, j = e / NZ;
-            double m = I.H[k * NZP + tri(i, j)];
-            if (i == j) {
-                m += dwreg;
-                if (!(k == 0 && j < NX)) {
-                    const int wi = k * NZ + j;
-                    const double lo = S.lbx[wi], hi = S.ubx[wi];
-                    if (fin(lo)) m += I.zL[wi] / (I.w[wi] - rlo(lo, rf));
-                    if (fin(hi)) m += I.zU[wi] / (rhi(hi, rf) - I.w[wi]);
-                }
-            }
+            double m = R[R_M + e] + (i == j ? dwreg : 0.0);
 #if NG > 0
-            for (int r = 0; r < NG; ++r) m += I.G[k * NG * NZ + r + NG * i] * sg[r] * I.G[k * NG * NZ + r + NG * j];
+            if (dwreg != 0.0) for (int r = 0; r < NG; ++r) m += dwreg * R[R_G + r + NG * i] * R[R_G + r + NG * j];
 #endif
-            for (int l = 0; l < NX; ++l) m += AB[l + NX * i] * T[l + NX * j];
+            for (int l = 0; l < NX; ++l) m += R[R_AB + l + NX * i] * T[l + NX * j];
             M[e] = m;
         }
         for (int i = lane; i < NZ; i += N_LANES) {
-            double a = I.gl[k * NZ + i];
-            if (!(k == 0 && i < NX)) {
-                const int wi = k * NZ + i;
-                const double lo = S.lbx[wi], hi = S.ubx[wi];
-                if (fin(lo)) a -= mu / (I.w[wi] - rlo(lo, rf));
-                if (fin(hi)) a += mu / (rhi(hi, rf) - I.w[wi]);
-            }
+            double a = R[R_GL + i] - mu * R[R_IL + i] + mu * R[R_IU + i];
 #if NG > 0
-            for (int r = 0; r < NG; ++r) a += I.G[k * NG * NZ + r + NG * i] * cf[r];
+            for (int r = 0; r < NG; ++r) a += R[R_G + r + NG * i] * cf[r];
 #endif
-            for (int l = 0; l < NX; ++l) a += AB[l + NX * i] * f[l];
+            for (int l = 0; l < NX; ++l) a += R[R_AB + l + NX * i] * f[l];
             q[i] = a;
         }
         W_SYNC();
-        // ---- (d) Cholesky of the input block M_uu = L L' (every lane, in registers)
-        double L[NU * NU];
+        // (d) Cholesky of the input block M_uu = L L' (every lane, in registers); Li = 1 / diag(L)
+        double L[NU * NU], Li[NU];
         bool pd = true;
         for (int j = 0; j < NU; ++j) {
             double djj = M[(NX + j) + NZ * (NX + j)];
             for (int l = 0; l < j; ++l) djj -= L[j + NU * l] * L[j + NU * l];
             if (!(djj > 0.0)) { pd = false; djj = 1.0; }
-            djj = sqrt(djj);
-            L[j + NU * j] = djj;
+            const double inv = 1.0 / sqrt(djj);
+            Li[j] = inv;
+            L[j + NU * j] = djj * inv;
             for (int i = j + 1; i < NU; ++i) {
                 double a = M[(NX + i) + NZ * (NX + j)];
                 for (int l = 0; l < j; ++l) a -= L[i + NU * l] * L[j + NU * l];
-                L[i + NU * j] = a / djj;
+                L[i + NU * j] = a * inv;
             }
         }
-        if (!pd) return false;                                   // uniform across the warp
-        // ---- (e) K = -Muu^{-1} Mux (NU x NX), kff = -Muu^{-1} q_u : one column per lane
+        if (!pd) return false;                                   // uniform across the lanes
+        // (e) K = -Muu^{-1} Mux (NU x NX), kff = -Muu^{-1} q_u : one column per lane
         for (int c = lane; c <= NX; c += N_LANES) {
             double y[NU];
             for (int i = 0; i < NU; ++i) {
                 double a = (c < NX) ? M[(NX + i) + NZ * c] : q[NX + i];
                 for (int l = 0; l < i; ++l) a -= L[i + NU * l] * y[l];
-                y[i] = a / L[i + NU * i];
+                y[i] = a * Li[i];
             }
             for (int i = NU - 1; i >= 0; --i) {
                 double a = y[i];
                 for (int l = i + 1; l < NU; ++l) a -= L[l + NU * i] * y[l];
-                y[i] = a / L[i + NU * i];
+                y[i] = a * Li[i];
             }
             for (int i = 0; i < NU; ++i) {
-                if (c < NX) { Kk[i + NU * c] = -y[i]; I.Kf[k * NU * NX + i + NU * c] = -y[i]; }
-                else { kk[i] = -y[i]; I.kf[k * NU + i] = -y[i]; }
+                if (c < NX) { Kk[i + NU * c] = -y[i]; fk[FREC_K + i + NU * c] = -y[i]; }
+                else { kk[i] = -y[i]; fk[FREC_KF + i] = -y[i]; }
             }
         }
         W_SYNC();
-        // ---- (f) P = Mxx + Mxu K (symmetrised), p = q_x + Mxu kff
+        // (f) P = Mxx + Mxu K (symmetrised), p = q_x + Mxu kff
         for (int e = lane; e < NX * NX; e += N_LANES) {
             const int i = e % NX, j = e / NX;
             double a = M[i + NZ * j], b = M[j + NZ * i];
             for (int l = 0; l < NU; ++l) { a += M[i + NZ * (NX + l)] * Kk[l + NU * j]; b += M[j + NZ * (NX + l)] * Kk[l + NU * i]; }
-            const double v = (i == j) ? a : 0.5 * (a + b);
-            P[e] = v;
-            I.Pm[k * NX * NX + e] = v;
+            P[e] = (i == j) ? a : 0.5 * (a + b);
         }
         for (int i = lane; i < NX; i += N_LANES) {
             double a = q[i];
             for (int l = 0; l < NU; ++l) a += M[i + NZ * (NX + l)] * kk[l];
             p[i] = a;
-            I.pv[k * NX + i] = a;
         }
         W_SYNC();
     }
     return true;
 }
 
-MPCB_HD void ocp_finish(OcpInst& I, const OcpShared& S, int status) {
+MPCB_HD void ocp_finish(OcpInst& I, const OcpShared& S, int status, double fval) {
     InstState& st = *I.st;
-    double f = 0.0;
-    for (int k = LANE_ID; k <= NH; k += N_LANES) f += I.part[k * 4 + 0];
-    f = W_SUM(f);
     if (S.o.honor_original_bounds)
         for (int i = NX + LANE_ID; i < NW; i += N_LANES) I.w[i] = fmin(fmax(I.w[i], S.lbx[i]), S.ubx[i]);
-    if (LANE_ID == 0) { st.status = status; st.state = ST_DONE; st.fval = f; }
+    if (LANE_ID == 0) { st.status = status; st.state = ST_DONE; st.fval = fval; }
     W_SYNC();
+}
+
+// Step-size bookkeeping for one bounded quantity with step dv, division free:
+//   primal fraction to the boundary  alpha <= tau (v-lo)/(-dv)   <=>  alpha <= tau / max(-iL dv, iU dv)
+//   dual   fraction to the boundary  alpha <= tau zL/(-dzL)      <=>  alpha <= tau / max(1 + iL dv - mu qL, 1 - iU dv - mu qU)
+//   (dzL = mu iL - zL - zL iL dv,  qL = iL / zL), and the barrier part of the directional derivative.
+MPCB_HD void step_terms(double dv, double iL, double iU, double qL, double qU, double mu,
+                        double* rp, double* rd, double* gphid) {
+    if (iL > 0.0) { *gphid -= mu * iL * dv; *rp = fmax(*rp, -iL * dv); *rd = fmax(*rd, 1.0 + iL * dv - mu * qL); }
+    if (iU > 0.0) { *gphid += mu * iU * dv; *rp = fmax(*rp, iU * dv); *rd = fmax(*rd, 1.0 - iU * dv - mu * qU); }
 }
 
 // =============================================================================================
@@ -510,44 +521,60 @@ MPCB_HD void ocp_kkt(OcpInst& I, const OcpShared& S, double* sm) {
     const double rf = S.o.bound_relax;
     const int lane = LANE_ID;
     const int iter = st.iter;
+    // ---- reduce the per-stage partials written by the evaluation
+    double fobj = 0.0, theta = 0.0, dual = 0.0, prim = 0.0, ysum = 0.0, zsum = 0.0, nbd = 0.0, pmin = 1e300, pmax = -1e300;
+    double barr = 0.0;
+    for (int k = lane; k <= NH; k += N_LANES) {
+        const double* pp = (k < NH) ? (I.rec + k * REC_SZ + R_PART) : (I.trec + T_PART);
+        fobj += pp[0]; theta += pp[1]; dual = fmax(dual, pp[2]); prim = fmax(prim, pp[3]); ysum += pp[4];
+        zsum += pp[5]; nbd += pp[6]; pmin = fmin(pmin, pp[7]); pmax = fmax(pmax, pp[8]); barr += pp[9];
+    }
+    fobj = W_SUM(fobj); theta = W_SUM(theta); dual = W_MAX(dual); prim = W_MAX(prim); ysum = W_SUM(ysum);
+    zsum = W_SUM(zsum); nbd = W_SUM(nbd); pmin = W_MIN(pmin); pmax = W_MAX(pmax); barr = W_SUM(barr);
 #if NG > 0
     // A stage-0 range row that does not depend on u_0 is a constant (x_0 is fixed).  Outside its relaxed
     // bounds the OCP is infeasible: IPOPT would end in restoration with Infeasible_Problem_Detected, the
     // one status the reference loop reacts to (MPC_code.py:786,804; quirk D7 of SURVEY.md).
     if (iter == 0) {
         bool infeasible = false;
+        const double* r0 = I.rec;
         for (int r = 0; r < NG; ++r) {
             bool constant = true;
-            for (int j = NX; j < NZ; ++j) if (I.G[r + NG * j] != 0.0) constant = false;
+            for (int j = NX; j < NZ; ++j) if (r0[R_G + r + NG * j] != 0.0) constant = false;
             if (!constant) continue;
-            const double v = I.gv[r], lo = S.lbg[r], hi = S.ubg[r];
+            const double v = r0[R_GV + r], lo = S.lbg[r], hi = S.ubg[r];
             if ((fin(lo) && v < rlo(lo, rf) - S.o.tol) || (fin(hi) && v > rhi(hi, rf) + S.o.tol)) infeasible = true;
         }
-        if (infeasible) { ocp_finish(I, S, 2); return; }
+        if (infeasible) { ocp_finish(I, S, 2, fobj); return; }
     }
 #endif
     // ---- optimality error and termination (IPOPT: tol, dual_inf_tol=1, constr_viol_tol=1e-4, compl_inf_tol=1e-4)
-    const KktErr e = ocp_errors(I, S);
-    const double c0 = ocp_compl(I, S, 0.0);
-    const double E0 = fmax(fmax(e.dual / e.sd, e.prim), c0 / e.sc);
+    const double smax = 100.0;
+    const double mc = (double)(NH * NX + NH * NG);
+    const double sd = fmax(smax, (ysum + zsum) / fmax(mc + nbd, 1.0)) / smax;
+    const double sc = fmax(smax, zsum / fmax(nbd, 1.0)) / smax;
+    const bool bounded = pmax >= pmin;
+    const double c0 = bounded ? fmax(fabs(pmax), fabs(pmin)) : 0.0;
+    const double E0 = fmax(fmax(dual / sd, prim), c0 / sc);
     int acc_cnt = st.acc_cnt;
     W_SYNC();
     if (lane == 0) st.E0 = E0;
-    if (!(E0 == E0) || !fin(E0)) { ocp_finish(I, S, -13); return; }
-    if (E0 <= S.o.tol && e.dual <= 1.0 && e.prim <= 1e-4 && c0 <= 1e-4) { ocp_finish(I, S, 0); return; }
-    if (E0 <= S.o.acceptable_tol && e.dual <= 1e10 && e.prim <= 1e-2 && c0 <= 1e-2) {
+    if (!(E0 == E0) || !fin(E0)) { ocp_finish(I, S, -13, fobj); return; }
+    if (E0 <= S.o.tol && dual <= 1.0 && prim <= 1e-4 && c0 <= 1e-4) { ocp_finish(I, S, 0, fobj); return; }
+    if (E0 <= S.o.acceptable_tol && dual <= 1e10 && prim <= 1e-2 && c0 <= 1e-2) {
         acc_cnt += 1;
-        if (acc_cnt >= S.o.acceptable_iter) { ocp_finish(I, S, 1); return; }
+        if (acc_cnt >= S.o.acceptable_iter) { ocp_finish(I, S, 1, fobj); return; }
     } else {
         acc_cnt = 0;
     }
-    if (iter >= S.o.max_iter) { ocp_finish(I, S, -1); return; }
+    if (iter >= S.o.max_iter) { ocp_finish(I, S, -1, fobj); return; }
     // ---- monotone barrier update (kappa_eps=10, kappa_mu=0.2, theta_mu=1.5)
     double mu = st.mu;
     const double mu_min = S.o.tol / 10.0;
     bool changed = false;
     while (mu > mu_min) {
-        const double Emu = fmax(fmax(e.dual / e.sd, e.prim), ocp_compl(I, S, mu) / e.sc);
+        const double cm = bounded ? fmax(fabs(pmax - mu), fabs(pmin - mu)) : 0.0;
+        const double Emu = fmax(fmax(dual / sd, prim), cm / sc);
         if (Emu > 10.0 * mu) break;
         mu = fmax(mu_min, fmin(0.2 * mu, pow(mu, 1.5)));
         changed = true;
@@ -560,98 +587,72 @@ MPCB_HD void ocp_kkt(OcpInst& I, const OcpShared& S, double* sm) {
     double dwreg = 0.0;
     bool first = true, ok = false;
     for (int attempt = 0; attempt < 60; ++attempt) {
-        if (ocp_riccati(I, S, mu, dwreg, sm)) { ok = true; break; }
+        if (ocp_riccati(I, mu, dwreg, sm)) { ok = true; break; }
         W_SYNC();
         if (first) { dwreg = (dw_last == 0.0) ? 1e-4 : fmax(1e-20, dw_last / 3.0); first = false; }
         else dwreg *= (dw_last == 0.0) ? 100.0 : 8.0;
         if (dwreg > 1e40) break;
     }
-    if (!ok) { ocp_finish(I, S, -3); return; }
-    // ---- forward sweep (sequential over the stages): dw and the new dynamics multipliers
+    if (!ok) { ocp_finish(I, S, -3, fobj); return; }
+    // ---- forward sweep (sequential over the stages): dw, the new multipliers, slack steps, and - fused -
+    //      fraction to the boundary (primal and dual), barrier objective and its directional derivative
     double* dx = sm + KktScratch::dx; double* du = sm + KktScratch::du; double* dxn = sm + KktScratch::dxn;
+    double rp = 0.0, rd = 0.0, gphid = 0.0;       // largest primal / dual boundary ratios, directional derivative
     for (int i = lane; i < NX; i += N_LANES) { dx[i] = 0.0; I.dw[i] = 0.0; }
     W_SYNC();
     for (int k = 0; k < NH; ++k) {
-        const double* A = I.A + k * NX * NX; const double* Bm = I.Bm + k * NX * NU;
+        const double* R = stage_record(I.rec + k * REC_SZ, sm, R_PART);
+        const double* F = I.frec + k * FREC_SZ;
         for (int i = lane; i < NU; i += N_LANES) {
-            double a = I.kf[k * NU + i];
-            for (int j = 0; j < NX; ++j) a += I.Kf[k * NU * NX + i + NU * j] * dx[j];
+            double a = F[FREC_KF + i];
+            for (int j = 0; j < NX; ++j) a += F[FREC_K + i + NU * j] * dx[j];
             du[i] = a;
             I.dw[k * NZ + NX + i] = a;
         }
         W_SYNC();
         for (int i = lane; i < NX; i += N_LANES) {
-            double a = I.c[k * NX + i];
-            for (int j = 0; j < NX; ++j) a += A[i + NX * j] * dx[j];
-            for (int j = 0; j < NU; ++j) a += Bm[i + NX * j] * du[j];
+            double a = R[R_C + i];
+            for (int j = 0; j < NX; ++j) a += R[R_AB + i + NX * j] * dx[j];
+            for (int j = 0; j < NU; ++j) a += R[R_AB + NX * NX + i + NX * j] * du[j];
             dxn[i] = a;
             I.dw[(k + 1) * NZ + i] = a;
         }
-        W_SYNC();
-        for (int i = lane; i < NX; i += N_LANES) {
-            double a = I.pv[(k + 1) * NX + i];
-            for (int j = 0; j < NX; ++j) a += I.Pm[(k + 1) * NX * NX + i + NX * j] * dxn[j];
-            I.lamn[k * NX + i] = a;
-            dx[i] = dxn[i];
+        // stage variables (x_k, u_k) against their bounds
+        for (int j = lane; j < NZ; j += N_LANES) {
+            const double dv = (j < NX) ? dx[j] : du[j - NX];
+            gphid += R[R_GL + j] * dv;
+            step_terms(dv, R[R_IL + j], R[R_IU + j], R[R_QL + j], R[R_QU + j], mu, &rp, &rd, &gphid);
         }
-        W_SYNC();
-    }
-    // ---- stage-parallel: slack / multiplier steps of the range rows, fraction to the boundary (primal and
-    //      dual), barrier objective and its directional derivative
-    double amax = 1.0, az = 1.0, gphid = 0.0, theta = 0.0, barr = 0.0, fobj = 0.0;
-    for (int k = lane; k <= NH; k += N_LANES) {
-        fobj += I.part[k * 4 + 0];
-        if (k < NH) theta += I.part[k * 4 + 1];
 #if NG > 0
-        if (k < NH) {
-            for (int r = 0; r < NG; ++r) {
-                const int gi = k * NG + r;
-                const double lo = S.lbg[gi], hi = S.ubg[gi];
-                double sig = dwreg, b = 0.0, dl = 1.0, du_ = 1.0;
-                if (fin(lo)) { dl = I.s[gi] - rlo(lo, rf); sig += I.vL[gi] / dl; b -= mu / dl; barr += log(dl); }
-                if (fin(hi)) { du_ = rhi(hi, rf) - I.s[gi]; sig += I.vU[gi] / du_; b += mu / du_; barr += log(du_); }
-                double dsr = I.gv[gi] - I.s[gi];
-                for (int j = 0; j < NZ; ++j) dsr += I.G[k * NG * NZ + r + NG * j] * I.dw[k * NZ + j];
-                I.ds[gi] = dsr;
-                I.dym[gi] = sig * dsr + b - I.ym[gi];
-                gphid += b * dsr;
-                if (fin(lo)) {
-                    if (dsr < 0.0) amax = fmin(amax, -tau * dl / dsr);
-                    const double dz = mu / dl - I.vL[gi] - I.vL[gi] / dl * dsr;
-                    if (dz < 0.0) az = fmin(az, -tau * I.vL[gi] / dz);
-                }
-                if (fin(hi)) {
-                    if (dsr > 0.0) amax = fmin(amax, tau * du_ / dsr);
-                    const double dz = mu / du_ - I.vU[gi] + I.vU[gi] / du_ * dsr;
-                    if (dz < 0.0) az = fmin(az, -tau * I.vU[gi] / dz);
-                }
-            }
+        for (int r = lane; r < NG; r += N_LANES) {
+            double dsr = R[R_RG + r];
+            for (int j = 0; j < NZ; ++j) dsr += R[R_G + r + NG * j] * ((j < NX) ? dx[j] : du[j - NX]);
+            const double b = -mu * R[R_ISL + r] + mu * R[R_ISU + r];
+            I.ds[k * NG + r] = dsr;
+            I.dym[k * NG + r] = (R[R_SG + r] + dwreg) * dsr + b - R[R_YM + r];
+            step_terms(dsr, R[R_ISL + r], R[R_ISU + r], R[R_QSL + r], R[R_QSU + r], mu, &rp, &rd, &gphid);
         }
 #endif
-        const int nz = (k == NH) ? NX : NZ;
-        for (int j = 0; j < nz; ++j) {
-            if (k == 0 && j < NX) continue;
-            const int wi = k * NZ + j;
-            const double dv = I.dw[wi];
-            gphid += ((k == NH) ? I.gN[j] : I.gl[k * NZ + j]) * dv;
-            const double lo = S.lbx[wi], hi = S.ubx[wi];
-            if (fin(lo)) {
-                const double dl = I.w[wi] - rlo(lo, rf);
-                barr += log(dl); gphid -= mu / dl * dv;
-                if (dv < 0.0) amax = fmin(amax, -tau * dl / dv);
-                const double dz = mu / dl - I.zL[wi] - I.zL[wi] / dl * dv;
-                if (dz < 0.0) az = fmin(az, -tau * I.zL[wi] / dz);
-            }
-            if (fin(hi)) {
-                const double du_ = rhi(hi, rf) - I.w[wi];
-                barr += log(du_); gphid += mu / du_ * dv;
-                if (dv > 0.0) amax = fmin(amax, tau * du_ / dv);
-                const double dz = mu / du_ - I.zU[wi] + I.zU[wi] / du_ * dv;
-                if (dz < 0.0) az = fmin(az, -tau * I.zU[wi] / dz);
-            }
+        W_SYNC();
+        for (int i = lane; i < NX; i += N_LANES) {
+            double a = F[FREC_PV + i];
+            for (int j = 0; j < NX; ++j) a += F[FREC_P + i + NX * j] * dxn[j];
+            I.lamn[k * NX + i] = a;
+        }
+        W_SYNC();
+        for (int i = lane; i < NX; i += N_LANES) dx[i] = dxn[i];
+        W_SYNC();
+    }
+    {
+        const double* t = I.trec;
+        for (int j = lane; j < NX; j += N_LANES) {
+            gphid += t[T_GN + j] * dx[j];
+            step_terms(dx[j], t[T_IL + j], t[T_IU + j], t[T_QL + j], t[T_QU + j], mu, &rp, &rd, &gphid);
         }
     }
-    amax = W_MIN(amax); az = W_MIN(az); gphid = W_SUM(gphid); theta = W_SUM(theta); barr = W_SUM(barr); fobj = W_SUM(fobj);
+    rp = W_MAX(rp); rd = W_MAX(rd); gphid = W_SUM(gphid);
+    const double amax = (rp > tau) ? tau / rp : 1.0;
+    const double az = (rd > tau) ? tau / rd : 1.0;
     const double phi = fobj - mu * barr;
     const double theta0 = (theta0_old < 0.0) ? theta : theta0_old;
     const double theta_min = 1e-4 * fmax(1.0, theta0);
@@ -670,7 +671,7 @@ MPCB_HD void ocp_kkt(OcpInst& I, const OcpShared& S, double* sm) {
         if (dwreg > 0.0) st.dw_last = dwreg;
         st.theta0 = theta0;
         st.amin = 0.05 * amin;
-        st.theta = theta; st.phi = phi; st.gphid = gphid;
+        st.theta = theta; st.phi = phi; st.gphid = gphid; st.fval = fobj;
         st.alpha = amax; st.alpha_z = az;
         st.ls_iter = 0;
         st.state = ST_LS;
@@ -691,7 +692,7 @@ MPCB_HD void ocp_trial_stage(OcpInst& I, const OcpShared& S, int k) {
     for (int i = 0; i < NU; ++i) u[i] = w[k * NZ + NX + i] + al * dw[k * NZ + NX + i];
     stage_params(I.par, k, d, px, py, &t0);
     dyn_value(x, u, d, px, t0, xn);
-    double th = 0.0, barr = 0.0, l;
+    double th = 0.0, prod = 1.0, l;     // prod: product of slacks-to-bounds (one log per stage)
 #pragma unroll
     for (int i = 0; i < NX; ++i) th += fabs(xn[i] - (w[(k + 1) * NZ + i] + al * dw[(k + 1) * NZ + i]));
     ocp_cost(x, u, I.par, px, py, &l);
@@ -704,8 +705,8 @@ MPCB_HD void ocp_trial_stage(OcpInst& I, const OcpShared& S, int k) {
             const double st_ = I.s[gi] + al * I.ds[gi];
             th += fabs(Y[i] - st_);
             const double lo = S.lbg[gi], hi = S.ubg[gi];
-            if (fin(lo)) barr += log(st_ - rlo(lo, rf));
-            if (fin(hi)) barr += log(rhi(hi, rf) - st_);
+            if (fin(lo)) prod *= st_ - rlo(lo, rf);
+            if (fin(hi)) prod *= rhi(hi, rf) - st_;
         }
     }
 #endif
@@ -713,27 +714,56 @@ MPCB_HD void ocp_trial_stage(OcpInst& I, const OcpShared& S, int k) {
         const int wi = k * NZ + j;
         const double v = (j < NX) ? x[j] : u[j - NX];
         const double lo = S.lbx[wi], hi = S.ubx[wi];
-        if (fin(lo)) barr += log(v - rlo(lo, rf));
-        if (fin(hi)) barr += log(rhi(hi, rf) - v);
+        if (fin(lo)) prod *= v - rlo(lo, rf);
+        if (fin(hi)) prod *= rhi(hi, rf) - v;
     }
-    I.partt[k * 4 + 0] = l; I.partt[k * 4 + 1] = th; I.partt[k * 4 + 2] = barr;
+    I.partt[k * 4 + 0] = l; I.partt[k * 4 + 1] = th; I.partt[k * 4 + 2] = log(prod);
     if (k == NH - 1) {
-        double xN[NX], V, bN = 0.0;
+        double xN[NX], V, pN = 1.0;
         for (int j = 0; j < NX; ++j) {
             const int wi = NH * NZ + j;
             xN[j] = w[wi] + al * dw[wi];
             const double lo = S.lbx[wi], hi = S.ubx[wi];
-            if (fin(lo)) bN += log(xN[j] - rlo(lo, rf));
-            if (fin(hi)) bN += log(rhi(hi, rf) - xN[j]);
+            if (fin(lo)) pN *= xN[j] - rlo(lo, rf);
+            if (fin(hi)) pN *= rhi(hi, rf) - xN[j];
         }
         ocp_term(xN, I.par, &V);
-        I.partt[NH * 4 + 0] = V; I.partt[NH * 4 + 1] = 0.0; I.partt[NH * 4 + 2] = bN;
+        I.partt[NH * 4 + 0] = V; I.partt[NH * 4 + 1] = 0.0; I.partt[NH * 4 + 2] = log(pN);
     }
 }
 
 // =============================================================================================
-// accept: filter line-search decision for one instance (lane-generic, see above)
+// accept: filter line-search decision for one instance.  Always one warp per instance on the device
+// (the updates are element-wise over w, lam, s, z), one lane on the host.
 // =============================================================================================
+#undef LANE_ID
+#undef N_LANES
+#undef W_SYNC
+#undef W_SUM
+#undef W_MAX
+#undef W_MIN
+#ifdef __CUDA_ARCH__
+#  define LANE_ID   ((int)(threadIdx.x & 31))
+#  define N_LANES   32
+#  define W_SYNC()  __syncwarp()
+#  define W_SUM(v)  warp_sum(v)
+#  define W_MAX(v)  warp_max(v)
+#  define W_MIN(v)  warp_min(v)
+#else
+#  define LANE_ID   0
+#  define N_LANES   1
+#  define W_SYNC()
+#  define W_SUM(v)  (v)
+#  define W_MAX(v)  (v)
+#  define W_MIN(v)  (v)
+#endif
+MPCB_HD void ocp_finish_w(OcpInst& I, const OcpShared& S, int status, double fval) {
+    InstState& st = *I.st;
+    if (S.o.honor_original_bounds)
+        for (int i = NX + LANE_ID; i < NW; i += N_LANES) I.w[i] = fmin(fmax(I.w[i], S.lbx[i]), S.ubx[i]);
+    if (LANE_ID == 0) { st.status = status; st.state = ST_DONE; st.fval = fval; }
+    W_SYNC();
+}
 MPCB_HD void ocp_accept(OcpInst& I, const OcpShared& S) {
     InstState& st = *I.st;
     const int lane = LANE_ID;
@@ -769,7 +799,7 @@ MPCB_HD void ocp_accept(OcpInst& I, const OcpShared& S) {
         // No restoration phase.  IPOPT would now minimise the constraint violation; when that cannot be reduced it
         // returns Infeasible_Problem_Detected (the status the reference loop acts on), so a failed line search away
         // from feasibility (violation above constr_viol_tol = 1e-4) is reported as 2, otherwise Restoration_Failed.
-        if (give_up) ocp_finish(I, S, theta > 1e-4 ? 2 : -2);
+        if (give_up) ocp_finish_w(I, S, theta > 1e-4 ? 2 : -2, st.fval);
         return;
     }
     // ---- take the step; bound multipliers with their own step size, then the kappa_sigma safeguard
