@@ -107,9 +107,12 @@ __global__ void __launch_bounds__(32 * KKT_WARPS) k_ocp_accept(OcpArgs a, int* n
 }
 
 __global__ void k_ocp_output(OcpArgs a, double* f, int* status, int* iters) {
-    const int inst = blockIdx.x * blockDim.x + threadIdx.x;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int inst = tid / (NH + 1), k = tid % (NH + 1);
     if (inst >= a.B) return;
-    f[inst] = a.st[inst].fval; status[inst] = a.st[inst].status; iters[inst] = a.st[inst].iter;
+    OcpInst I = ocp_view(a, inst);
+    ocp_export_stage(I, k);                 // internal iterate -> caller's w (reference layout)
+    if (k == 0) { f[inst] = a.st[inst].fval; status[inst] = a.st[inst].status; iters[inst] = a.st[inst].iter; }
 }
 
 // stage derivatives alone (mpcb_stage_derivs)
@@ -306,7 +309,7 @@ int mpcb_create(int batch, const mpcb_opts_t* oss, const mpcb_opts_t* odyn, mpcb
     CK(cudaMalloc(&h->ws, sizeof(double) * (size_t)batch * OcpLayout::total));
     CK(cudaMemset(h->ws, 0, sizeof(double) * (size_t)batch * OcpLayout::total));
     CK(cudaMalloc(&h->st, sizeof(InstState) * (size_t)batch));
-    CK(cudaMalloc(&h->lbx, sizeof(double) * NW)); CK(cudaMalloc(&h->ubx, sizeof(double) * NW));
+    CK(cudaMalloc(&h->lbx, sizeof(double) * NWI)); CK(cudaMalloc(&h->ubx, sizeof(double) * NWI));
     CK(cudaMalloc(&h->lbg, sizeof(double) * (NH * NGS))); CK(cudaMalloc(&h->ubg, sizeof(double) * (NH * NGS)));
 #endif
     h->ss_lbx = h->ss_ubx = nullptr;
@@ -340,9 +343,23 @@ int mpcb_destroy(mpcb_handle_t h) {
 const char* mpcb_last_error(mpcb_handle_t h) { return h ? h->err.c_str() : "null handle"; }
 
 int mpcb_set_const(mpcb_handle_t h, const char* name, const double* p, int n) {
+#if MPCB_HAS_OCP
+    if (!strcmp(name, "ocp_lbx") || !strcmp(name, "ocp_ubx")) {
+        // reference layout [x0,u0,...,xN] -> internal layout [z0,u0,...,zN], z = [x; v]; the carried inputs v are free
+        if (n != NW) { h->err = std::string("mpcb_set_const: wrong length for ") + name; return -2; }
+        const bool lower = !strcmp(name, "ocp_lbx");
+        std::vector<double> tmp(NWI, lower ? -INFINITY : INFINITY);
+        for (int k = 0; k <= NH; ++k) {
+            for (int i = 0; i < NX; ++i) tmp[k * NZA + i] = p[k * NZ + i];
+            if (k < NH) for (int i = 0; i < NU; ++i) tmp[k * NZA + NXA + i] = p[k * NZ + NX + i];
+        }
+        CK(cudaMemcpy(lower ? h->lbx : h->ubx, tmp.data(), sizeof(double) * NWI, cudaMemcpyHostToDevice));
+        return 0;
+    }
+#endif
     struct { const char* nm; double* dst; int len; } tab[] = {
 #if MPCB_HAS_OCP
-        {"ocp_lbx", h->lbx, NW}, {"ocp_ubx", h->ubx, NW}, {"ocp_lbg", h->lbg, NH * NG}, {"ocp_ubg", h->ubg, NH * NG},
+        {"ocp_lbg", h->lbg, NH * NG}, {"ocp_ubg", h->ubg, NH * NG},
 #endif
 #if MPCB_HAS_TARGET
         {"ss_lbx", h->ss_lbx, NWS}, {"ss_ubx", h->ss_ubx, NWS},
@@ -390,7 +407,7 @@ int mpcb_ocp(mpcb_handle_t h, const double* par, double* w, double* f, int* stat
         prof_collect(h);
         if (*h->h_active == 0) break;
     }
-    { Prof p(h, s, KC_OTHER); k_ocp_output<<<nblk(h->B, 128), 128, 0, s>>>(a, f, status, iters); } launches++;
+    { Prof p(h, s, KC_OTHER); k_ocp_output<<<nblk((long)h->B * (NH + 1), 128), 128, 0, s>>>(a, f, status, iters); } launches++;
     CK(cudaGetLastError());
     if (h->profile) {
         unsigned long long cnt[2];

@@ -18,6 +18,14 @@
 #include "mpcb_device.cuh"
 
 #define NG   MPCB_NG
+// The OCP may carry u_{k-1} as extra state components (Delta-u costs / Delta-u bounds, Control_Calc.py:163-169,
+// 180-181): stage state z_k = [x_k; v_k], v_k = u_{k-1}, with the linear rows v_{k+1} = u_k.  NAUG = nu or 0.
+#define NAUG MPCB_NAUG
+#define NXA  (NX + NAUG)                  // stage state size seen by the Riccati recursion
+#define NZA  (NXA + NU)
+#define NZAP (NZA * (NZA + 1) / 2)
+#define NXAP (NXA * (NXA + 1) / 2)
+#define NWI  (NH * NZA + NXA)             // internal iterate [z_0,u_0,...,z_N]; the caller's w keeps the reference layout
 #define NW   MPCB_NW
 #define NPAR MPCB_NPAR
 #define MPCB_MAXFILT 24
@@ -38,7 +46,7 @@ struct InstState {
 
 // Per-instance view of the solver workspace (all device pointers).
 struct OcpInst {
-    double* w; const double* par;
+    double* w; double* wext; const double* par;      // w: internal iterate (NWI); wext: caller buffer (NW, reference layout)
     double *lam, *lamn, *s, *ds, *ym, *dym, *zL, *zU, *vL, *vU, *dw;
     double *rec, *trec, *frec, *partt;
     InstState* st;
@@ -49,18 +57,18 @@ struct OcpShared { const double *lbx, *ubx, *lbg, *ubg; IpmOpts o; };
 // k_ocp_eval condenses everything the Newton step needs from stage k into ONE contiguous record, so that the
 // sequential sweeps of the KKT step stream memory instead of gathering from a dozen arrays:
 #define NGS (NG > 0 ? NG : 1)
-#define R_AB   0                          // NX*NZ  [A_k | B_k], column-major
-#define R_C    (R_AB + NX * NZ)           // NX     defect  Fx(x_k,u_k) - x_{k+1}
-#define R_M    (R_C + NX)                 // NZ*NZ  H_k + diag(zL/dL + zU/dU) + G' Sigma_s G   (delta_w = 0)
-#define R_GL   (R_M + NZ * NZ)            // NZ     gradient of the stage cost
-#define R_IL   (R_GL + NZ)                // NZ     1 / (v - lo)  (0: no lower bound / fixed x_0)
-#define R_IU   (R_IL + NZ)                // NZ     1 / (hi - v)
-#define R_ZL   (R_IU + NZ)                // NZ
-#define R_ZU   (R_ZL + NZ)                // NZ
-#define R_QL   (R_ZU + NZ)                // NZ     (1/(v-lo)) / zL   (0: no bound) - keeps the step-size rules division free
-#define R_QU   (R_QL + NZ)                // NZ     (1/(hi-v)) / zU
-#define R_G    (R_QU + NZ)                // NG*NZ  Jacobian of the range rows (column-major NG x NZ)
-#define R_SG   (R_G + NGS * NZ)           // NG     Sigma_s = vL/(s-lo) + vU/(hi-s)
+#define R_AB   0                          // NXA*NZA  [A_k | B_k], column-major
+#define R_C    (R_AB + NXA * NZA)           // NXA     defect  Fx(x_k,u_k) - x_{k+1}
+#define R_M    (R_C + NXA)                 // NZA*NZA  H_k + diag(zL/dL + zU/dU) + G' Sigma_s G   (delta_w = 0)
+#define R_GL   (R_M + NZA * NZA)            // NZA     gradient of the stage cost
+#define R_IL   (R_GL + NZA)                // NZA     1 / (v - lo)  (0: no lower bound / fixed x_0)
+#define R_IU   (R_IL + NZA)                // NZA     1 / (hi - v)
+#define R_ZL   (R_IU + NZA)                // NZA
+#define R_ZU   (R_ZL + NZA)                // NZA
+#define R_QL   (R_ZU + NZA)                // NZA     (1/(v-lo)) / zL   (0: no bound) - keeps the step-size rules division free
+#define R_QU   (R_QL + NZA)                // NZA     (1/(hi-v)) / zU
+#define R_G    (R_QU + NZA)                // NG*NZA  Jacobian of the range rows (column-major NG x NZA)
+#define R_SG   (R_G + NGS * NZA)           // NG     Sigma_s = vL/(s-lo) + vU/(hi-s)
 #define R_ISL  (R_SG + NGS)               // NG     1 / (s - lo)
 #define R_ISU  (R_ISL + NGS)              // NG     1 / (hi - s)
 #define R_VL   (R_ISU + NGS)              // NG
@@ -74,45 +82,46 @@ struct OcpShared { const double *lbx, *ubx, *lbg, *ubg; IpmOpts o; };
 #define NPART  10
 #define REC_SZ ((R_PART + NPART + 1) / 2 * 2)
 // terminal record (x_N)
-#define T_H    0                          // NX*NX  Hessian of the terminal cost
-#define T_GN   (NX * NX)                  // NX     its gradient
-#define T_IL   (T_GN + NX)
-#define T_IU   (T_IL + NX)
-#define T_ZL   (T_IU + NX)
-#define T_ZU   (T_ZL + NX)
-#define T_QL   (T_ZU + NX)
-#define T_QU   (T_QL + NX)
-#define T_PART (T_QU + NX)                // 10: V, 0, dual_max, 0, 0, zsum, nb, pmin, pmax, sum log(slack)
+#define T_H    0                          // NXA*NXA  Hessian of the terminal cost
+#define T_GN   (NXA * NXA)                  // NXA     its gradient
+#define T_IL   (T_GN + NXA)
+#define T_IU   (T_IL + NXA)
+#define T_ZL   (T_IU + NXA)
+#define T_ZU   (T_ZL + NXA)
+#define T_QL   (T_ZU + NXA)
+#define T_QU   (T_QL + NXA)
+#define T_PART (T_QU + NXA)                // 10: V, 0, dual_max, 0, 0, zsum, nb, pmin, pmax, sum log(slack)
 #define TREC_SZ ((T_PART + NPART + 1) / 2 * 2)
 // forward records written by the Riccati sweep
 #define FREC_K   0
-#define FREC_KF  (NU * NX)
+#define FREC_KF  (NU * NXA)
 #define FREC_P   (FREC_KF + NU)
-#define FREC_PV  (FREC_P + NX * NX)
-#define FREC_SZ  ((FREC_PV + NX + 1) / 2 * 2)
+#define FREC_PV  (FREC_P + NXA * NXA)
+#define FREC_SZ  ((FREC_PV + NXA + 1) / 2 * 2)
 
 struct OcpLayout {
     static constexpr int lam = 0;
-    static constexpr int lamn = lam + NH * NX;
-    static constexpr int s = lamn + NH * NX;
+    static constexpr int lamn = lam + NH * NXA;
+    static constexpr int s = lamn + NH * NXA;
     static constexpr int ds = s + NH * NGS;
     static constexpr int ym = ds + NH * NGS;
     static constexpr int dym = ym + NH * NGS;
     static constexpr int vL = dym + NH * NGS;
     static constexpr int vU = vL + NH * NGS;
     static constexpr int zL = vU + NH * NGS;
-    static constexpr int zU = zL + NW;
-    static constexpr int dw = zU + NW;
-    static constexpr int rec = (dw + NW + 1) / 2 * 2;
+    static constexpr int zU = zL + NWI;
+    static constexpr int dw = zU + NWI;
+    static constexpr int wint = (dw + NWI + 1) / 2 * 2;
+    static constexpr int rec = (wint + NWI + 1) / 2 * 2;
     static constexpr int trec = rec + NH * REC_SZ;
     static constexpr int frec = trec + TREC_SZ;
     static constexpr int partt = frec + NH * FREC_SZ;
     static constexpr int total = (partt + (NH + 1) * 4 + 1) / 2 * 2;
 };
 
-MPCB_HD OcpInst ocp_inst(double* ws, double* w, const double* par, InstState* st) {
+MPCB_HD OcpInst ocp_inst(double* ws, double* wext, const double* par, InstState* st) {
     OcpInst I;
-    I.w = w; I.par = par; I.st = st;
+    I.w = ws + OcpLayout::wint; I.wext = wext; I.par = par; I.st = st;
     I.lam = ws + OcpLayout::lam; I.lamn = ws + OcpLayout::lamn; I.s = ws + OcpLayout::s; I.ds = ws + OcpLayout::ds;
     I.ym = ws + OcpLayout::ym; I.dym = ws + OcpLayout::dym; I.vL = ws + OcpLayout::vL; I.vU = ws + OcpLayout::vU;
     I.zL = ws + OcpLayout::zL; I.zU = ws + OcpLayout::zU; I.dw = ws + OcpLayout::dw;
@@ -153,35 +162,49 @@ MPCB_HD void stage_params(const double* par, int k, double* d, double* px, doubl
 }
 
 // =============================================================================================
-// init: starting point (IPOPT default initialisation), one call per (instance, stage k=0..NH)
+// init: starting point (IPOPT default initialisation), one call per (instance, stage k=0..NH).
+// Copies the caller's guess (reference layout) into the internal iterate z_k = [x_k; v_k], u_k.
 // =============================================================================================
+MPCB_HD double init_push(const OcpShared& S, int wi, double v) {       // push component wi of the internal iterate inside
+    const double rf = S.o.bound_relax, lo = S.lbx[wi], hi = S.ubx[wi];
+    return push_in(v, fin(lo) ? rlo(lo, rf) : lo, fin(hi) ? rhi(hi, rf) : hi, S.o.bound_push);
+}
+
 MPCB_HD void ocp_init_stage(OcpInst& I, const OcpShared& S, int k) {
     const double rf = S.o.bound_relax, kp = S.o.bound_push;
     double* w = I.w;
+    const double* we = I.wext;
     if (k == 0) {
-#pragma unroll
-        for (int i = 0; i < NX; ++i) { w[i] = I.par[MPCB_OFF_X0 + i]; I.zL[i] = 0.0; I.zU[i] = 0.0; }   // MPC_code.py:734
         InstState& st = *I.st;
         st.mu = S.o.mu_init; st.tau = fmax(0.99, 1.0 - S.o.mu_init);
         st.alpha = st.alpha_z = 0.0; st.theta0 = -1.0; st.dw_last = 0.0; st.fval = 0.0; st.E0 = 0.0;
         st.state = ST_EVAL; st.iter = 0; st.status = -1; st.nfilt = 0; st.acc_cnt = 0; st.ls_iter = 0;
     }
-    const int lo_i = (k == 0) ? NX : k * NZ;
-    const int hi_i = (k == NH) ? NH * NZ + NX : (k + 1) * NZ;
-    for (int i = lo_i; i < hi_i; ++i) {
-        const double lo = S.lbx[i], hi = S.ubx[i];
-        const double lor = fin(lo) ? rlo(lo, rf) : lo, hir = fin(hi) ? rhi(hi, rf) : hi;
-        w[i] = push_in(w[i], lor, hir, kp);
-        I.zL[i] = fin(lo) ? 1.0 : 0.0;
-        I.zU[i] = fin(hi) ? 1.0 : 0.0;
+    // state part z_k = [x_k; v_k]
+    for (int i = 0; i < NXA; ++i) {
+        const int wi = k * NZA + i;
+        double v;
+        if (i < NX) v = (k == 0) ? I.par[MPCB_OFF_X0 + i] : we[k * NZ + i];                     // MPC_code.py:734
+        else v = (k == 0) ? I.par[MPCB_OFF_UM1 + (i - NX)]                                      // Control_Calc.py:163-164
+                          : init_push(S, (k - 1) * NZA + NXA + (i - NX), we[(k - 1) * NZ + NX + (i - NX)]);   // = pushed u_{k-1}
+        if (k == 0) { w[wi] = v; I.zL[wi] = 0.0; I.zU[wi] = 0.0; continue; }                    // z_0 is fixed
+        w[wi] = init_push(S, wi, v);
+        I.zL[wi] = fin(S.lbx[wi]) ? 1.0 : 0.0;
+        I.zU[wi] = fin(S.ubx[wi]) ? 1.0 : 0.0;
     }
     if (k < NH) {
+        for (int i = 0; i < NU; ++i) {
+            const int wi = k * NZA + NXA + i;
+            w[wi] = init_push(S, wi, we[k * NZ + NX + i]);
+            I.zL[wi] = fin(S.lbx[wi]) ? 1.0 : 0.0;
+            I.zU[wi] = fin(S.ubx[wi]) ? 1.0 : 0.0;
+        }
 #pragma unroll
-        for (int i = 0; i < NX; ++i) I.lam[k * NX + i] = 0.0;
+        for (int i = 0; i < NXA; ++i) I.lam[k * NXA + i] = 0.0;
 #if NG > 0
         double d[ND + 1], px[NPX + 1], py[NPY + 1], t0, Y[NG];
         stage_params(I.par, k, d, px, py, &t0);
-        ocp_out(w + k * NZ, w + k * NZ + NX, I.par, py, Y);
+        ocp_out(w + k * NZA, w + k * NZA + NXA, I.par, py, Y);
         for (int i = 0; i < NG; ++i) {
             const double lo = S.lbg[k * NG + i], hi = S.ubg[k * NG + i];
             const double lor = fin(lo) ? rlo(lo, rf) : lo, hir = fin(hi) ? rhi(hi, rf) : hi;
@@ -192,6 +215,12 @@ MPCB_HD void ocp_init_stage(OcpInst& I, const OcpShared& S, int k) {
         }
 #endif
     }
+}
+
+// copy the internal iterate back into the caller's buffer (reference layout)
+MPCB_HD void ocp_export_stage(OcpInst& I, int k) {
+    for (int i = 0; i < NX; ++i) I.wext[k * NZ + i] = I.w[k * NZA + i];
+    if (k < NH) for (int i = 0; i < NU; ++i) I.wext[k * NZ + NX + i] = I.w[k * NZA + NXA + i];
 }
 
 // =============================================================================================
@@ -212,59 +241,94 @@ MPCB_HD void bound_terms(double v, double lo, double hi, double zl, double zu, d
 MPCB_HD void ocp_eval_stage(OcpInst& I, const OcpShared& S, int k) {
     const double* w = I.w;
     const double rf = S.o.bound_relax;
-    double x[NX], u[NU], lam[NX], d[ND + 1], px[NPX + 1], py[NPY + 1], t0;
+    double z[NXA], u[NU], lam[NXA], d[ND + 1], px[NPX + 1], py[NPY + 1], t0;
 #pragma unroll
-    for (int i = 0; i < NX; ++i) { x[i] = w[k * NZ + i]; lam[i] = I.lam[k * NX + i]; }
+    for (int i = 0; i < NXA; ++i) { z[i] = w[k * NZA + i]; lam[i] = I.lam[k * NXA + i]; }
 #pragma unroll
-    for (int i = 0; i < NU; ++i) u[i] = w[k * NZ + NX + i];
+    for (int i = 0; i < NU; ++i) u[i] = w[k * NZA + NXA + i];
     stage_params(I.par, k, d, px, py, &t0);
-    double xn[NX], A[NX * NX], Bm[NX * NU], Hp[NZP], l, g[NZ];
-    ocp_cost_d(x, u, I.par, px, py, &l, g, Hp);          // Hp <- cost Hessian, then accumulate the rest
-    dyn_full(x, u, d, px, t0, lam, xn, A, Bm, Hp);
+    double xn[NXA], A[NXA * NXA], Bm[NXA * NU], Hp[NZAP], l, g[NZA];
+    ocp_cost_d(z, u, I.par, px, py, &l, g, Hp);          // Hp <- cost Hessian, then accumulate the rest
+#if NAUG == 0
+    dyn_full(z, u, d, px, t0, lam, xn, A, Bm, Hp);
+#else
+    {   // model part by the RK4 sweeps, then embedded into the augmented stage:  z+ = [Fx(x,u); u]
+        double xm[NX], Am[NX * NX], Bmm[NX * NU], Hm[NZP];
+#pragma unroll
+        for (int i = 0; i < NZP; ++i) Hm[i] = 0.0;
+        dyn_full(z, u, d, px, t0, lam, xm, Am, Bmm, Hm);
+#pragma unroll
+        for (int i = 0; i < NXA * NXA; ++i) A[i] = 0.0;
+#pragma unroll
+        for (int i = 0; i < NXA * NU; ++i) Bm[i] = 0.0;
+#pragma unroll
+        for (int j = 0; j < NX; ++j)
+#pragma unroll
+            for (int i = 0; i < NX; ++i) A[i + NXA * j] = Am[i + NX * j];
+#pragma unroll
+        for (int j = 0; j < NU; ++j) {
+#pragma unroll
+            for (int i = 0; i < NX; ++i) Bm[i + NXA * j] = Bmm[i + NX * j];
+            Bm[NX + j + NXA * j] = 1.0;
+        }
+#pragma unroll
+        for (int i = 0; i < NX; ++i) xn[i] = xm[i];
+#pragma unroll
+        for (int i = 0; i < NU; ++i) xn[NX + i] = u[i];
+        // model Hessian (ordering x,u) into the augmented ordering (x, v, u)
+#pragma unroll
+        for (int i = 0; i < NZ; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j) {
+                const int ia = (i < NX) ? i : i + NAUG, ja = (j < NX) ? j : j + NAUG;
+                Hp[tri(ia, ja)] += Hm[tri(i, j)];
+            }
+    }
+#endif
     double* r = I.rec + k * REC_SZ;
     double th = 0.0, prim = 0.0, ysum = 0.0, zsum = 0.0, nb = 0.0, pmin = 1e300, pmax = -1e300;
     double prod = 1.0;     // product of all slacks-to-bounds of the stage: one log instead of one per bound
 #pragma unroll
-    for (int i = 0; i < NX; ++i) {
-        const double ci = xn[i] - w[(k + 1) * NZ + i];
+    for (int i = 0; i < NXA; ++i) {
+        const double ci = xn[i] - w[(k + 1) * NZA + i];
         r[R_C + i] = ci;
         th += fabs(ci); prim = fmax(prim, fabs(ci)); ysum += fabs(lam[i]);
     }
     // dual residual of the stage variables, started with the cost gradient and the dynamics multipliers
-    double res[NZ], dg[NZ];
+    double res[NZA], dg[NZA];
 #pragma unroll
-    for (int j = 0; j < NZ; ++j) {
+    for (int j = 0; j < NZA; ++j) {
         double a = g[j];
 #pragma unroll
-        for (int i = 0; i < NX; ++i) a += ((j < NX) ? A[i + NX * j] : Bm[i + NX * (j - NX)]) * lam[i];
-        if (j < NX && k > 0) a -= I.lam[(k - 1) * NX + j];
+        for (int i = 0; i < NXA; ++i) a += ((j < NXA) ? A[i + NXA * j] : Bm[i + NXA * (j - NXA)]) * lam[i];
+        if (j < NXA && k > 0) a -= I.lam[(k - 1) * NXA + j];
         res[j] = a; dg[j] = 0.0;
     }
 #pragma unroll
-    for (int j = 0; j < NZ; ++j) {
-        const int wi = k * NZ + j;
-        const bool active = !(k == 0 && j < NX);          // x_0 is fixed
+    for (int j = 0; j < NZA; ++j) {
+        const int wi = k * NZA + j;
+        const bool active = !(k == 0 && j < NXA);          // x_0 is fixed
         double iL, iU, zL, zU, qL, qU;
         bound_terms(w[wi], S.lbx[wi], S.ubx[wi], I.zL[wi], I.zU[wi], rf, active, &iL, &iU, &zL, &zU, &qL, &qU, &dg[j], &zsum, &nb, &pmin, &pmax, &prod);
         r[R_IL + j] = iL; r[R_IU + j] = iU; r[R_ZL + j] = zL; r[R_ZU + j] = zU; r[R_QL + j] = qL; r[R_QU + j] = qU; r[R_GL + j] = g[j];
         res[j] += zU - zL;
     }
-    double M[NZ * NZ], dual_s = 0.0;
+    double M[NZA * NZA], dual_s = 0.0;
 #pragma unroll
-    for (int j = 0; j < NZ; ++j)
+    for (int j = 0; j < NZA; ++j)
 #pragma unroll
-        for (int i = 0; i < NZ; ++i) M[i + NZ * j] = Hp[tri(i, j)] + (i == j ? dg[j] : 0.0);
+        for (int i = 0; i < NZA; ++i) M[i + NZA * j] = Hp[tri(i, j)] + (i == j ? dg[j] : 0.0);
 #if NG > 0
     {
-        double Y[NG], JY[NG * NZ], HY[NZP], mult[NG];
+        double Y[NG], JY[NG * NZA], HY[NZAP], mult[NG];
 #pragma unroll
         for (int i = 0; i < NG; ++i) mult[i] = I.ym[k * NG + i];
-        ocp_out_d(x, u, I.par, py, mult, Y, JY, HY);
+        ocp_out_d(z, u, I.par, py, mult, Y, JY, HY);
 #if !MPCB_OUT_LINEAR
 #pragma unroll
-        for (int j = 0; j < NZ; ++j)
+        for (int j = 0; j < NZA; ++j)
 #pragma unroll
-            for (int i = 0; i < NZ; ++i) M[i + NZ * j] += HY[tri(i, j)];
+            for (int i = 0; i < NZA; ++i) M[i + NZA * j] += HY[tri(i, j)];
 #endif
 #pragma unroll
         for (int q = 0; q < NG; ++q) {
@@ -279,40 +343,41 @@ MPCB_HD void ocp_eval_stage(OcpInst& I, const OcpShared& S, int k) {
             th += fabs(rg); prim = fmax(prim, fabs(rg)); ysum += fabs(mult[q]);
             dual_s = fmax(dual_s, fabs(-mult[q] - vl + vu));   // dual residual of the slack
 #pragma unroll
-            for (int j = 0; j < NZ; ++j) {
+            for (int j = 0; j < NZA; ++j) {
                 r[R_G + q + NG * j] = JY[q + NG * j];
                 res[j] += JY[q + NG * j] * mult[q];
 #pragma unroll
-                for (int i = 0; i < NZ; ++i) M[i + NZ * j] += JY[q + NG * i] * sig * JY[q + NG * j];
+                for (int i = 0; i < NZA; ++i) M[i + NZA * j] += JY[q + NG * i] * sig * JY[q + NG * j];
             }
         }
     }
 #endif
     double dual = dual_s;
 #pragma unroll
-    for (int j = 0; j < NZ; ++j) if (!(k == 0 && j < NX)) dual = fmax(dual, fabs(res[j]));
+    for (int j = 0; j < NZA; ++j) if (!(k == 0 && j < NXA)) dual = fmax(dual, fabs(res[j]));
 #pragma unroll
-    for (int i = 0; i < NX * NX; ++i) r[R_AB + i] = A[i];
+    for (int i = 0; i < NXA * NXA; ++i) r[R_AB + i] = A[i];
 #pragma unroll
-    for (int i = 0; i < NX * NU; ++i) r[R_AB + NX * NX + i] = Bm[i];
+    for (int i = 0; i < NXA * NU; ++i) r[R_AB + NXA * NXA + i] = Bm[i];
 #pragma unroll
-    for (int i = 0; i < NZ * NZ; ++i) r[R_M + i] = M[i];
+    for (int i = 0; i < NZA * NZA; ++i) r[R_M + i] = M[i];
     r[R_PART + 0] = l; r[R_PART + 1] = th; r[R_PART + 2] = dual; r[R_PART + 3] = prim; r[R_PART + 4] = ysum;
     r[R_PART + 5] = zsum; r[R_PART + 6] = nb; r[R_PART + 7] = pmin; r[R_PART + 8] = pmax; r[R_PART + 9] = log(prod);
     if (k == NH - 1) {
         double V, gN[NX], HN[NXP_ + 1];
         double* t = I.trec;
-        ocp_term_d(w + NH * NZ, I.par, &V, gN, HN);
+        ocp_term_d(w + NH * NZA, I.par, &V, gN, HN);           // terminal cost acts on x_N only (Control_Calc.py:194-196,209)
         double dualN = 0.0, zs = 0.0, nbn = 0.0, pmn = 1e300, pmx = -1e300, prodN = 1.0;
 #pragma unroll
-        for (int j = 0; j < NX; ++j) {
-            const int wi = NH * NZ + j;
+        for (int j = 0; j < NXA; ++j) {
+            const int wi = NH * NZA + j;
             double iL, iU, zL, zU, qL, qU, sig = 0.0;
             bound_terms(w[wi], S.lbx[wi], S.ubx[wi], I.zL[wi], I.zU[wi], rf, true, &iL, &iU, &zL, &zU, &qL, &qU, &sig, &zs, &nbn, &pmn, &pmx, &prodN);
-            t[T_IL + j] = iL; t[T_IU + j] = iU; t[T_ZL + j] = zL; t[T_ZU + j] = zU; t[T_QL + j] = qL; t[T_QU + j] = qU; t[T_GN + j] = gN[j];
-            dualN = fmax(dualN, fabs(gN[j] - lam[j] + zU - zL));          // lam = lam_N for k = NH-1
+            const double gj = (j < NX) ? gN[j] : 0.0;
+            t[T_IL + j] = iL; t[T_IU + j] = iU; t[T_ZL + j] = zL; t[T_ZU + j] = zU; t[T_QL + j] = qL; t[T_QU + j] = qU; t[T_GN + j] = gj;
+            dualN = fmax(dualN, fabs(gj - lam[j] + zU - zL));          // lam = lam_N for k = NH-1
 #pragma unroll
-            for (int i = 0; i < NX; ++i) t[T_H + i + NX * j] = HN[tri(i, j)];
+            for (int i = 0; i < NXA; ++i) t[T_H + i + NXA * j] = (i < NX && j < NX) ? HN[tri(i, j)] : 0.0;
         }
         t[T_PART + 0] = V; t[T_PART + 1] = 0.0; t[T_PART + 2] = dualN; t[T_PART + 3] = 0.0; t[T_PART + 4] = 0.0;
         t[T_PART + 5] = zs; t[T_PART + 6] = nbn; t[T_PART + 7] = pmn; t[T_PART + 8] = pmx; t[T_PART + 9] = log(prodN);
@@ -351,19 +416,19 @@ MPCB_HD void ocp_eval_stage(OcpInst& I, const OcpShared& S, int k) {
 // scratch (doubles): shared memory per warp with 32 lanes, thread-local (registers) with one lane
 struct KktScratch {
     static constexpr int R = 0;                                     // staged record (32-lane mapping only)
-    static constexpr int P = R + (MPCB_KKT_LANES == 32 ? REC_SZ : 0);   // NX x NX  cost-to-go Hessian of the next stage
-    static constexpr int p = P + NX * NX;             // NX
-    static constexpr int M = p + NX;                  // NZ x NZ  condensed stage Hessian
-    static constexpr int q = M + NZ * NZ;             // NZ
-    static constexpr int T = q + NZ;                  // NX x NZ  P [A B]
-    static constexpr int f = T + NX * NZ;             // NX       P c + p
-    static constexpr int K = f + NX;                  // NU x NX
-    static constexpr int kk = K + NU * NX;            // NU
+    static constexpr int P = R + (MPCB_KKT_LANES == 32 ? REC_SZ : 0);   // NXA x NXA  cost-to-go Hessian of the next stage
+    static constexpr int p = P + NXA * NXA;             // NXA
+    static constexpr int M = p + NXA;                  // NZA x NZA  condensed stage Hessian
+    static constexpr int q = M + NZA * NZA;             // NZA
+    static constexpr int T = q + NZA;                  // NXA x NZA  P [A B]
+    static constexpr int f = T + NXA * NZA;             // NXA       P c + p
+    static constexpr int K = f + NXA;                  // NU x NXA
+    static constexpr int kk = K + NU * NXA;            // NU
     static constexpr int cf = kk + NU;                // NGS      slack gradient coefficient
-    static constexpr int dx = cf + NGS;               // NX
-    static constexpr int du = dx + NX;                // NU
-    static constexpr int dxn = du + NU;               // NX
-    static constexpr int total = dxn + NX;
+    static constexpr int dx = cf + NGS;               // NXA
+    static constexpr int du = dx + NXA;                // NU
+    static constexpr int dxn = du + NU;               // NXA
+    static constexpr int total = dxn + NXA;
 };
 
 // Make the record of a stage readable by all lanes: staged through shared memory for a warp, read in place
@@ -391,54 +456,54 @@ MPCB_HD bool ocp_riccati(OcpInst& I, double mu, double dwreg, double* sm) {
     // ---- terminal stage
     {
         const double* t = I.trec;
-        for (int e = lane; e < NX * NX; e += N_LANES) {
-            const int i = e % NX, j = e / NX;
+        for (int e = lane; e < NXA * NXA; e += N_LANES) {
+            const int i = e % NXA, j = e / NXA;
             double v = t[T_H + e];
             if (i == j) v += dwreg + t[T_ZL + i] * t[T_IL + i] + t[T_ZU + i] * t[T_IU + i];
             P[e] = v;
         }
-        for (int i = lane; i < NX; i += N_LANES) p[i] = t[T_GN + i] - mu * t[T_IL + i] + mu * t[T_IU + i];
+        for (int i = lane; i < NXA; i += N_LANES) p[i] = t[T_GN + i] - mu * t[T_IL + i] + mu * t[T_IU + i];
     }
     W_SYNC();
     for (int k = NH - 1; k >= 0; --k) {
         const double* R = stage_record(I.rec + k * REC_SZ, sm, R_PART);
         double* fk = I.frec + k * FREC_SZ;
         // (a) P_{k+1}, p_{k+1} go to the forward record; slack coefficients
-        for (int e = lane; e < NX * NX; e += N_LANES) fk[FREC_P + e] = P[e];
-        for (int e = lane; e < NX; e += N_LANES) fk[FREC_PV + e] = p[e];
+        for (int e = lane; e < NXA * NXA; e += N_LANES) fk[FREC_P + e] = P[e];
+        for (int e = lane; e < NXA; e += N_LANES) fk[FREC_PV + e] = p[e];
 #if NG > 0
         for (int r = lane; r < NG; r += N_LANES)
             cf[r] = (R[R_SG + r] + dwreg) * R[R_RG + r] - mu * R[R_ISL + r] + mu * R[R_ISU + r];
 #endif
         // (b) f = P c + p ;  T = P [A B]
-        for (int i = lane; i < NX; i += N_LANES) {
+        for (int i = lane; i < NXA; i += N_LANES) {
             double a = p[i];
-            for (int j = 0; j < NX; ++j) a += P[i + NX * j] * R[R_C + j];
+            for (int j = 0; j < NXA; ++j) a += P[i + NXA * j] * R[R_C + j];
             f[i] = a;
         }
-        for (int e = lane; e < NX * NZ; e += N_LANES) {
-            const int i = e % NX, j = e / NX;
+        for (int e = lane; e < NXA * NZA; e += N_LANES) {
+            const int i = e % NXA, j = e / NXA;
             double a = 0.0;
-            for (int l = 0; l < NX; ++l) a += P[i + NX * l] * R[R_AB + l + NX * j];
+            for (int l = 0; l < NXA; ++l) a += P[i + NXA * l] * R[R_AB + l + NXA * j];
             T[e] = a;
         }
         W_SYNC();
         // (c) M = M0 + dw (I + G'G) + [A B]' P [A B] ;  q = grad - mu/dL + mu/dU + G' cf + [A B]' f
-        for (int e = lane; e < NZ * NZ; e += N_LANES) {
-            const int i = e % NZ, j = e / NZ;
+        for (int e = lane; e < NZA * NZA; e += N_LANES) {
+            const int i = e % NZA, j = e / NZA;
             double m = R[R_M + e] + (i == j ? dwreg : 0.0);
 #if NG > 0
             if (dwreg != 0.0) for (int r = 0; r < NG; ++r) m += dwreg * R[R_G + r + NG * i] * R[R_G + r + NG * j];
 #endif
-            for (int l = 0; l < NX; ++l) m += R[R_AB + l + NX * i] * T[l + NX * j];
+            for (int l = 0; l < NXA; ++l) m += R[R_AB + l + NXA * i] * T[l + NXA * j];
             M[e] = m;
         }
-        for (int i = lane; i < NZ; i += N_LANES) {
+        for (int i = lane; i < NZA; i += N_LANES) {
             double a = R[R_GL + i] - mu * R[R_IL + i] + mu * R[R_IU + i];
 #if NG > 0
             for (int r = 0; r < NG; ++r) a += R[R_G + r + NG * i] * cf[r];
 #endif
-            for (int l = 0; l < NX; ++l) a += R[R_AB + l + NX * i] * f[l];
+            for (int l = 0; l < NXA; ++l) a += R[R_AB + l + NXA * i] * f[l];
             q[i] = a;
         }
         W_SYNC();
@@ -446,24 +511,24 @@ MPCB_HD bool ocp_riccati(OcpInst& I, double mu, double dwreg, double* sm) {
         double L[NU * NU], Li[NU];
         bool pd = true;
         for (int j = 0; j < NU; ++j) {
-            double djj = M[(NX + j) + NZ * (NX + j)];
+            double djj = M[(NXA + j) + NZA * (NXA + j)];
             for (int l = 0; l < j; ++l) djj -= L[j + NU * l] * L[j + NU * l];
             if (!(djj > 0.0)) { pd = false; djj = 1.0; }
             const double inv = 1.0 / sqrt(djj);
             Li[j] = inv;
             L[j + NU * j] = djj * inv;
             for (int i = j + 1; i < NU; ++i) {
-                double a = M[(NX + i) + NZ * (NX + j)];
+                double a = M[(NXA + i) + NZA * (NXA + j)];
                 for (int l = 0; l < j; ++l) a -= L[i + NU * l] * L[j + NU * l];
                 L[i + NU * j] = a * inv;
             }
         }
         if (!pd) return false;                                   // uniform across the lanes
-        // (e) K = -Muu^{-1} Mux (NU x NX), kff = -Muu^{-1} q_u : one column per lane
-        for (int c = lane; c <= NX; c += N_LANES) {
+        // (e) K = -Muu^{-1} Mux (NU x NXA), kff = -Muu^{-1} q_u : one column per lane
+        for (int c = lane; c <= NXA; c += N_LANES) {
             double y[NU];
             for (int i = 0; i < NU; ++i) {
-                double a = (c < NX) ? M[(NX + i) + NZ * c] : q[NX + i];
+                double a = (c < NXA) ? M[(NXA + i) + NZA * c] : q[NXA + i];
                 for (int l = 0; l < i; ++l) a -= L[i + NU * l] * y[l];
                 y[i] = a * Li[i];
             }
@@ -473,21 +538,21 @@ MPCB_HD bool ocp_riccati(OcpInst& I, double mu, double dwreg, double* sm) {
                 y[i] = a * Li[i];
             }
             for (int i = 0; i < NU; ++i) {
-                if (c < NX) { Kk[i + NU * c] = -y[i]; fk[FREC_K + i + NU * c] = -y[i]; }
+                if (c < NXA) { Kk[i + NU * c] = -y[i]; fk[FREC_K + i + NU * c] = -y[i]; }
                 else { kk[i] = -y[i]; fk[FREC_KF + i] = -y[i]; }
             }
         }
         W_SYNC();
         // (f) P = Mxx + Mxu K (symmetrised), p = q_x + Mxu kff
-        for (int e = lane; e < NX * NX; e += N_LANES) {
-            const int i = e % NX, j = e / NX;
-            double a = M[i + NZ * j], b = M[j + NZ * i];
-            for (int l = 0; l < NU; ++l) { a += M[i + NZ * (NX + l)] * Kk[l + NU * j]; b += M[j + NZ * (NX + l)] * Kk[l + NU * i]; }
+        for (int e = lane; e < NXA * NXA; e += N_LANES) {
+            const int i = e % NXA, j = e / NXA;
+            double a = M[i + NZA * j], b = M[j + NZA * i];
+            for (int l = 0; l < NU; ++l) { a += M[i + NZA * (NXA + l)] * Kk[l + NU * j]; b += M[j + NZA * (NXA + l)] * Kk[l + NU * i]; }
             P[e] = (i == j) ? a : 0.5 * (a + b);
         }
-        for (int i = lane; i < NX; i += N_LANES) {
+        for (int i = lane; i < NXA; i += N_LANES) {
             double a = q[i];
-            for (int l = 0; l < NU; ++l) a += M[i + NZ * (NX + l)] * kk[l];
+            for (int l = 0; l < NU; ++l) a += M[i + NZA * (NXA + l)] * kk[l];
             p[i] = a;
         }
         W_SYNC();
@@ -498,7 +563,7 @@ MPCB_HD bool ocp_riccati(OcpInst& I, double mu, double dwreg, double* sm) {
 MPCB_HD void ocp_finish(OcpInst& I, const OcpShared& S, int status, double fval) {
     InstState& st = *I.st;
     if (S.o.honor_original_bounds)
-        for (int i = NX + LANE_ID; i < NW; i += N_LANES) I.w[i] = fmin(fmax(I.w[i], S.lbx[i]), S.ubx[i]);
+        for (int i = NXA + LANE_ID; i < NWI; i += N_LANES) I.w[i] = fmin(fmax(I.w[i], S.lbx[i]), S.ubx[i]);
     if (LANE_ID == 0) { st.status = status; st.state = ST_DONE; st.fval = fval; }
     W_SYNC();
 }
@@ -540,7 +605,7 @@ MPCB_HD void ocp_kkt(OcpInst& I, const OcpShared& S, double* sm) {
         const double* r0 = I.rec;
         for (int r = 0; r < NG; ++r) {
             bool constant = true;
-            for (int j = NX; j < NZ; ++j) if (r0[R_G + r + NG * j] != 0.0) constant = false;
+            for (int j = NXA; j < NZA; ++j) if (r0[R_G + r + NG * j] != 0.0) constant = false;
             if (!constant) continue;
             const double v = r0[R_GV + r], lo = S.lbg[r], hi = S.ubg[r];
             if ((fin(lo) && v < rlo(lo, rf) - S.o.tol) || (fin(hi) && v > rhi(hi, rf) + S.o.tol)) infeasible = true;
@@ -550,7 +615,7 @@ MPCB_HD void ocp_kkt(OcpInst& I, const OcpShared& S, double* sm) {
 #endif
     // ---- optimality error and termination (IPOPT: tol, dual_inf_tol=1, constr_viol_tol=1e-4, compl_inf_tol=1e-4)
     const double smax = 100.0;
-    const double mc = (double)(NH * NX + NH * NG);
+    const double mc = (double)(NH * NXA + NH * NG);
     const double sd = fmax(smax, (ysum + zsum) / fmax(mc + nbd, 1.0)) / smax;
     const double sc = fmax(smax, zsum / fmax(nbd, 1.0)) / smax;
     const bool bounded = pmax >= pmin;
@@ -598,35 +663,35 @@ MPCB_HD void ocp_kkt(OcpInst& I, const OcpShared& S, double* sm) {
     //      fraction to the boundary (primal and dual), barrier objective and its directional derivative
     double* dx = sm + KktScratch::dx; double* du = sm + KktScratch::du; double* dxn = sm + KktScratch::dxn;
     double rp = 0.0, rd = 0.0, gphid = 0.0;       // largest primal / dual boundary ratios, directional derivative
-    for (int i = lane; i < NX; i += N_LANES) { dx[i] = 0.0; I.dw[i] = 0.0; }
+    for (int i = lane; i < NXA; i += N_LANES) { dx[i] = 0.0; I.dw[i] = 0.0; }
     W_SYNC();
     for (int k = 0; k < NH; ++k) {
         const double* R = stage_record(I.rec + k * REC_SZ, sm, R_PART);
         const double* F = I.frec + k * FREC_SZ;
         for (int i = lane; i < NU; i += N_LANES) {
             double a = F[FREC_KF + i];
-            for (int j = 0; j < NX; ++j) a += F[FREC_K + i + NU * j] * dx[j];
+            for (int j = 0; j < NXA; ++j) a += F[FREC_K + i + NU * j] * dx[j];
             du[i] = a;
-            I.dw[k * NZ + NX + i] = a;
+            I.dw[k * NZA + NXA + i] = a;
         }
         W_SYNC();
-        for (int i = lane; i < NX; i += N_LANES) {
+        for (int i = lane; i < NXA; i += N_LANES) {
             double a = R[R_C + i];
-            for (int j = 0; j < NX; ++j) a += R[R_AB + i + NX * j] * dx[j];
-            for (int j = 0; j < NU; ++j) a += R[R_AB + NX * NX + i + NX * j] * du[j];
+            for (int j = 0; j < NXA; ++j) a += R[R_AB + i + NXA * j] * dx[j];
+            for (int j = 0; j < NU; ++j) a += R[R_AB + NXA * NXA + i + NXA * j] * du[j];
             dxn[i] = a;
-            I.dw[(k + 1) * NZ + i] = a;
+            I.dw[(k + 1) * NZA + i] = a;
         }
         // stage variables (x_k, u_k) against their bounds
-        for (int j = lane; j < NZ; j += N_LANES) {
-            const double dv = (j < NX) ? dx[j] : du[j - NX];
+        for (int j = lane; j < NZA; j += N_LANES) {
+            const double dv = (j < NXA) ? dx[j] : du[j - NXA];
             gphid += R[R_GL + j] * dv;
             step_terms(dv, R[R_IL + j], R[R_IU + j], R[R_QL + j], R[R_QU + j], mu, &rp, &rd, &gphid);
         }
 #if NG > 0
         for (int r = lane; r < NG; r += N_LANES) {
             double dsr = R[R_RG + r];
-            for (int j = 0; j < NZ; ++j) dsr += R[R_G + r + NG * j] * ((j < NX) ? dx[j] : du[j - NX]);
+            for (int j = 0; j < NZA; ++j) dsr += R[R_G + r + NG * j] * ((j < NXA) ? dx[j] : du[j - NXA]);
             const double b = -mu * R[R_ISL + r] + mu * R[R_ISU + r];
             I.ds[k * NG + r] = dsr;
             I.dym[k * NG + r] = (R[R_SG + r] + dwreg) * dsr + b - R[R_YM + r];
@@ -634,18 +699,18 @@ MPCB_HD void ocp_kkt(OcpInst& I, const OcpShared& S, double* sm) {
         }
 #endif
         W_SYNC();
-        for (int i = lane; i < NX; i += N_LANES) {
+        for (int i = lane; i < NXA; i += N_LANES) {
             double a = F[FREC_PV + i];
-            for (int j = 0; j < NX; ++j) a += F[FREC_P + i + NX * j] * dxn[j];
-            I.lamn[k * NX + i] = a;
+            for (int j = 0; j < NXA; ++j) a += F[FREC_P + i + NXA * j] * dxn[j];
+            I.lamn[k * NXA + i] = a;
         }
         W_SYNC();
-        for (int i = lane; i < NX; i += N_LANES) dx[i] = dxn[i];
+        for (int i = lane; i < NXA; i += N_LANES) dx[i] = dxn[i];
         W_SYNC();
     }
     {
         const double* t = I.trec;
-        for (int j = lane; j < NX; j += N_LANES) {
+        for (int j = lane; j < NXA; j += N_LANES) {
             gphid += t[T_GN + j] * dx[j];
             step_terms(dx[j], t[T_IL + j], t[T_IU + j], t[T_QL + j], t[T_QU + j], mu, &rp, &rd, &gphid);
         }
@@ -685,21 +750,23 @@ MPCB_HD void ocp_kkt(OcpInst& I, const OcpShared& S, double* sm) {
 MPCB_HD void ocp_trial_stage(OcpInst& I, const OcpShared& S, int k) {
     const double al = I.st->alpha, rf = S.o.bound_relax;
     const double* w = I.w; const double* dw = I.dw;
-    double x[NX], u[NU], d[ND + 1], px[NPX + 1], py[NPY + 1], t0, xn[NX];
+    double z[NXA], u[NU], d[ND + 1], px[NPX + 1], py[NPY + 1], t0, xn[NXA];
 #pragma unroll
-    for (int i = 0; i < NX; ++i) x[i] = w[k * NZ + i] + al * dw[k * NZ + i];
+    for (int i = 0; i < NXA; ++i) z[i] = w[k * NZA + i] + al * dw[k * NZA + i];
 #pragma unroll
-    for (int i = 0; i < NU; ++i) u[i] = w[k * NZ + NX + i] + al * dw[k * NZ + NX + i];
+    for (int i = 0; i < NU; ++i) u[i] = w[k * NZA + NXA + i] + al * dw[k * NZA + NXA + i];
     stage_params(I.par, k, d, px, py, &t0);
-    dyn_value(x, u, d, px, t0, xn);
+    dyn_value(z, u, d, px, t0, xn);
+#pragma unroll
+    for (int i = NX; i < NXA; ++i) xn[i] = u[i - NX];
     double th = 0.0, prod = 1.0, l;     // prod: product of slacks-to-bounds (one log per stage)
 #pragma unroll
-    for (int i = 0; i < NX; ++i) th += fabs(xn[i] - (w[(k + 1) * NZ + i] + al * dw[(k + 1) * NZ + i]));
-    ocp_cost(x, u, I.par, px, py, &l);
+    for (int i = 0; i < NXA; ++i) th += fabs(xn[i] - (w[(k + 1) * NZA + i] + al * dw[(k + 1) * NZA + i]));
+    ocp_cost(z, u, I.par, px, py, &l);
 #if NG > 0
     {
         double Y[NG];
-        ocp_out(x, u, I.par, py, Y);
+        ocp_out(z, u, I.par, py, Y);
         for (int i = 0; i < NG; ++i) {
             const int gi = k * NG + i;
             const double st_ = I.s[gi] + al * I.ds[gi];
@@ -710,18 +777,18 @@ MPCB_HD void ocp_trial_stage(OcpInst& I, const OcpShared& S, int k) {
         }
     }
 #endif
-    for (int j = (k == 0 ? NX : 0); j < NZ; ++j) {
-        const int wi = k * NZ + j;
-        const double v = (j < NX) ? x[j] : u[j - NX];
+    for (int j = (k == 0 ? NXA : 0); j < NZA; ++j) {
+        const int wi = k * NZA + j;
+        const double v = (j < NXA) ? z[j] : u[j - NXA];
         const double lo = S.lbx[wi], hi = S.ubx[wi];
         if (fin(lo)) prod *= v - rlo(lo, rf);
         if (fin(hi)) prod *= rhi(hi, rf) - v;
     }
     I.partt[k * 4 + 0] = l; I.partt[k * 4 + 1] = th; I.partt[k * 4 + 2] = log(prod);
     if (k == NH - 1) {
-        double xN[NX], V, pN = 1.0;
-        for (int j = 0; j < NX; ++j) {
-            const int wi = NH * NZ + j;
+        double xN[NXA], V, pN = 1.0;
+        for (int j = 0; j < NXA; ++j) {
+            const int wi = NH * NZA + j;
             xN[j] = w[wi] + al * dw[wi];
             const double lo = S.lbx[wi], hi = S.ubx[wi];
             if (fin(lo)) pN *= xN[j] - rlo(lo, rf);
@@ -760,7 +827,7 @@ MPCB_HD void ocp_trial_stage(OcpInst& I, const OcpShared& S, int k) {
 MPCB_HD void ocp_finish_w(OcpInst& I, const OcpShared& S, int status, double fval) {
     InstState& st = *I.st;
     if (S.o.honor_original_bounds)
-        for (int i = NX + LANE_ID; i < NW; i += N_LANES) I.w[i] = fmin(fmax(I.w[i], S.lbx[i]), S.ubx[i]);
+        for (int i = NXA + LANE_ID; i < NWI; i += N_LANES) I.w[i] = fmin(fmax(I.w[i], S.lbx[i]), S.ubx[i]);
     if (LANE_ID == 0) { st.status = status; st.state = ST_DONE; st.fval = fval; }
     W_SYNC();
 }
@@ -804,7 +871,7 @@ MPCB_HD void ocp_accept(OcpInst& I, const OcpShared& S) {
     }
     // ---- take the step; bound multipliers with their own step size, then the kappa_sigma safeguard
     const double ks = 1e10;
-    for (int i = NX + lane; i < NW; i += N_LANES) {
+    for (int i = NXA + lane; i < NWI; i += N_LANES) {
         const double lo = S.lbx[i], hi = S.ubx[i], dv = I.dw[i];
         const double wn = I.w[i] + alpha * dv;
         if (fin(lo)) {
@@ -819,7 +886,7 @@ MPCB_HD void ocp_accept(OcpInst& I, const OcpShared& S) {
         }
         I.w[i] = wn;
     }
-    for (int i = lane; i < NH * NX; i += N_LANES) I.lam[i] += alpha * (I.lamn[i] - I.lam[i]);
+    for (int i = lane; i < NH * NXA; i += N_LANES) I.lam[i] += alpha * (I.lamn[i] - I.lam[i]);
 #if NG > 0
     for (int i = lane; i < NH * NG; i += N_LANES) {
         const double lo = S.lbg[i], hi = S.ubg[i], dv = I.ds[i];

@@ -138,18 +138,22 @@ def generate_header(prob, ss_spec, ocp_spec, opts: Optional[Dict] = None) -> Dic
     # ---- OCP stage maps (Control_Calc.py:124-210) ---------------------------
     if ocp_spec is not None:
         o = ocp_spec
-        if o.uses_uprev:
-            raise NotImplementedError("Delta-u costs / Delta-u bounds (DUForm, DUFormEcon, Dumin/Dumax) are not on the device path yet")
         if o.flags["ContForm"] is True:
             raise NotImplementedError("ContForm (integrated stage cost) is not on the device path yet")
         if o.term_eq is not None:
             raise NotImplementedError("TermCons (terminal equality) is not on the device path yet")
-        D.update(MPCB_HAS_OCP=1, MPCB_NW=o.nw, MPCB_NPAR=o.npar, MPCB_NG=(0 if o.yFree else o.p))
+        # Delta-u costs / bounds couple u_k with u_{k-1} (Control_Calc.py:163-169,180-183): the device carries
+        # u_{k-1} as extra state components v_k (z_k = [x_k; v_k], v_{k+1} = u_k), so every stage map stays local.
+        naug = m_ = o.m if o.uses_uprev else 0
+        n_rows = (0 if o.yFree else o.p) + (0 if o.DuFree else o.m)
+        D.update(MPCB_HAS_OCP=1, MPCB_NW=o.nw, MPCB_NPAR=o.npar, MPCB_NG=n_rows, MPCB_NAUG=naug,
+                 MPCB_NGY=(0 if o.yFree else o.p), MPCB_NGDU=(0 if o.DuFree else o.m))
         for k_, v_ in o.off.items():
             D["MPCB_OFF_%s" % k_.upper()] = v_
         X, U, Up, par, pxk, pyk = o.X, o.U, o.Uprev, o.par, o.pxk, o.pyk
-        zz = vertcat(X, U)
-        ins_c = [("X", X), ("U", U), ("par", par), ("pxk", pxk), ("pyk", pyk)]
+        Z = vertcat(X, Up) if naug else X               # stage state seen by the kernels
+        zz = vertcat(Z, U)
+        ins_c = [("Z", Z), ("U", U), ("par", par), ("pxk", pxk), ("pyk", pyk)]
         Hc, gc = hessian(o.stage_cost, zz)
         fns.append(CFunction("ocp_cost", ins_c, [("l", o.stage_cost)]))
         fns.append(CFunction("ocp_cost_d", ins_c, [("l", o.stage_cost), ("g", gc), ("H", tril_pack(Hc))]))
@@ -157,13 +161,19 @@ def generate_header(prob, ss_spec, ocp_spec, opts: Optional[Dict] = None) -> Dic
         fns.append(CFunction("ocp_term", [("XN", o.XN), ("par", par)], [("V", o.term_cost)]))
         fns.append(CFunction("ocp_term_d", [("XN", o.XN), ("par", par)],
                              [("V", o.term_cost), ("g", gt), ("H", tril_pack(Ht))]))
-        if not o.yFree:
-            mult = SX.sym("mult", o.p)
-            Hy, _ = hessian(mtimes(mult.T, o.Y), zz)
-            ins_y = [("X", X), ("U", U), ("par", par), ("pyk", pyk)]
-            fns.append(CFunction("ocp_out", ins_y, [("Y", o.Y)]))
+        if n_rows:
+            rows = []
+            if not o.yFree:
+                rows.append(o.Y)
+            if not o.DuFree:
+                rows.append(o.DU)
+            R = vertcat(*rows)
+            mult = SX.sym("mult", n_rows)
+            Hy, _ = hessian(mtimes(mult.T, R), zz)
+            ins_y = [("Z", Z), ("U", U), ("par", par), ("pyk", pyk)]
+            fns.append(CFunction("ocp_out", ins_y, [("Y", R)]))
             fns.append(CFunction("ocp_out_d", ins_y + [("mult", mult)],
-                                 [("Y", o.Y), ("JY", jacobian(o.Y, zz)), ("HY", tril_pack(Hy))]))
+                                 [("Y", R), ("JY", jacobian(R, zz)), ("HY", tril_pack(Hy))]))
             D["MPCB_OUT_LINEAR"] = int(all(e is S.ZERO for e in Hy.elements()))
     else:
         D["MPCB_HAS_OCP"] = 0

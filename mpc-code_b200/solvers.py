@@ -291,8 +291,17 @@ class BatchedNlpSolver:
             if np.any(lbg[:n_dyn] != 0.0) or np.any(ubg[:n_dyn] != 0.0):
                 raise ValueError("the dynamics rows of g must stay equalities (lbg = ubg = 0)")
             h.set_const("ocp_lbx", lbx); h.set_const("ocp_ubx", ubx)
+            # g = [dynamics | Y_k rows (all k) | DU_k rows (all k)]  (Control_Calc.py:200-204,254) -> stage-interleaved
             ny_rows = 0 if s.yFree else s.p * s.N
-            h.set_const("ocp_lbg", lbg[n_dyn:n_dyn + ny_rows]); h.set_const("ocp_ubg", ubg[n_dyn:n_dyn + ny_rows])
+            ndu_rows = 0 if s.DuFree else s.m * s.N
+            def per_stage(v):
+                blocks = []
+                if ny_rows:
+                    blocks.append(v[n_dyn:n_dyn + ny_rows].reshape(s.N, s.p))
+                if ndu_rows:
+                    blocks.append(v[n_dyn + ny_rows:n_dyn + ny_rows + ndu_rows].reshape(s.N, s.m))
+                return np.hstack(blocks).reshape(-1) if blocks else np.zeros(0)
+            h.set_const("ocp_lbg", per_stage(lbg)); h.set_const("ocp_ubg", per_stage(ubg))
         else:
             if np.any(lbg != 0.0) or np.any(ubg != 0.0):
                 raise ValueError("the target problem's g rows are equalities (lbg = ubg = 0)")

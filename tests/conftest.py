@@ -61,7 +61,7 @@ class Bundle:
     def harness(self):
         if self._harness is None:
             res = self.lib
-            path = os.path.join(os.path.dirname(res["so"]), "harness_%s_%s.so" % (self.name, res["digest"]))
+            path = entry.harness_path(res, self.name)
             if not os.path.exists(path):
                 entry.build_harness(os.path.dirname(res["header"]), path)
             self._harness = ctypes.CDLL(path)
@@ -85,10 +85,20 @@ class Bundle:
         return w
 
     def ocp_range_bounds(self):
+        """Range rows of g_lb/g_ub stage by stage: [Y_k bounds, DU_k bounds] for k = 0..N-1 (see include/mpcb.h)."""
         o = self.ocp
         n_dyn = o.n * (o.N + 1)
         ny_rows = 0 if o.yFree else o.p * o.N
-        return (np.ascontiguousarray(o.g_lb[n_dyn:n_dyn + ny_rows]), np.ascontiguousarray(o.g_ub[n_dyn:n_dyn + ny_rows]))
+        ndu_rows = 0 if o.DuFree else o.m * o.N
+
+        def per_stage(v):
+            blocks = []
+            if ny_rows:
+                blocks.append(v[n_dyn:n_dyn + ny_rows].reshape(o.N, o.p))
+            if ndu_rows:
+                blocks.append(v[n_dyn + ny_rows:n_dyn + ny_rows + ndu_rows].reshape(o.N, o.m))
+            return np.ascontiguousarray(np.hstack(blocks).reshape(-1)) if blocks else np.zeros(0)
+        return per_stage(o.g_lb), per_stage(o.g_ub)
 
     def harness_ocp(self, par, w0, max_iter=100, tol=1e-8, mu_init=0.1, relax=1e-8, honor=0):
         H = self.harness
@@ -121,8 +131,22 @@ class Bundle:
 _BUNDLES = {}
 
 
+def _bundle(name):
+    if name not in _BUNDLES:
+        _BUNDLES[name] = Bundle(name)
+    return _BUNDLES[name]
+
+
 @pytest.fixture(scope="session")
 def nmpc():
-    if "nmpc_cstr" not in _BUNDLES:
-        _BUNDLES["nmpc_cstr"] = Bundle("nmpc_cstr")
-    return _BUNDLES["nmpc_cstr"]
+    return _bundle("nmpc_cstr")
+
+
+@pytest.fixture(scope="session")
+def lmpc_cstr():
+    return _bundle("lmpc_cstr")
+
+
+@pytest.fixture(scope="session")
+def lmpc_wb():
+    return _bundle("lmpc_wb")

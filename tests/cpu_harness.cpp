@@ -58,7 +58,13 @@ void h_stage_derivs(int B, const double* par, const double* w, const double* lam
 int h_ocp(int B, const double* par, double* w, double* f, int* status, int* iters,
           const double* lbx, const double* ubx, const double* lbg, const double* ubg,
           int max_iter, double tol, double mu_init, double relax, int honor, int* ticks_out) {
-    OcpShared S; S.lbx = lbx; S.ubx = ubx; S.lbg = lbg; S.ubg = ubg; S.o = mk_opts(max_iter, tol, mu_init, relax, honor);
+    // bounds: reference layout -> internal layout (as mpcb_set_const does)
+    std::vector<double> lbi(NWI, -INFINITY), ubi(NWI, INFINITY);
+    for (int k = 0; k <= NH; ++k) {
+        for (int i = 0; i < NX; ++i) { lbi[k * NZA + i] = lbx[k * NZ + i]; ubi[k * NZA + i] = ubx[k * NZ + i]; }
+        if (k < NH) for (int i = 0; i < NU; ++i) { lbi[k * NZA + NXA + i] = lbx[k * NZ + NX + i]; ubi[k * NZA + NXA + i] = ubx[k * NZ + NX + i]; }
+    }
+    OcpShared S; S.lbx = lbi.data(); S.ubx = ubi.data(); S.lbg = lbg; S.ubg = ubg; S.o = mk_opts(max_iter, tol, mu_init, relax, honor);
     std::vector<double> ws((size_t)B * OcpLayout::total, 0.0);
     std::vector<InstState> st(B);
     auto view = [&](int inst) { return ocp_inst(ws.data() + (size_t)inst * OcpLayout::total, w + (size_t)inst * NW,
@@ -78,7 +84,11 @@ int h_ocp(int B, const double* par, double* w, double* f, int* status, int* iter
         ticks++;
         if (!active) break;
     }
-    for (int inst = 0; inst < B; ++inst) { f[inst] = st[inst].fval; status[inst] = st[inst].status; iters[inst] = st[inst].iter; }
+    for (int inst = 0; inst < B; ++inst) {
+        OcpInst I = view(inst);
+        for (int k = 0; k <= NH; ++k) ocp_export_stage(I, k);
+        f[inst] = st[inst].fval; status[inst] = st[inst].status; iters[inst] = st[inst].iter;
+    }
     if (ticks_out) *ticks_out = ticks;
     return 0;
 }

@@ -105,6 +105,17 @@ def main():
     for key in ("U", "X_HAT", "D_HAT", "XS", "US", "Xp", "Yp", "F_DYN", "ITER_DYN", "STATUS_DYN"):
         out["cl_" + key] = np.stack([r[key] for r in recs], axis=1)
     np.savez_compressed(os.path.join(HERE, "nmpc_oracle.npz"), **out)
+    # ---- the two linear configurations: closed loop of the unmodified reference files (single instance, as shipped)
+    lin = {}
+    for fname, tag, Ns in (("Ex_LMPC_CSTR.py", "cstr", 24), ("Ex_LMPC_WB.py", "wb", 20)):
+        prob_l = build_problem(load_example(os.path.join(REF, fname)))
+        ss_l, ocp_l = make_specs(prob_l)
+        mod_l = cmodel.build("ref_" + tag, prob_l, ocp_l, ss_l)
+        rec = OracleLoop(prob_l, ss_l, ocp_l, mod_l).run(Nsim=Ns)
+        print(fname, "status", rec["STATUS_DYN"], "iters", rec["ITER_DYN"])
+        for key in ("U", "X_HAT", "D_HAT", "XS", "US", "Xp", "Yp", "F_DYN", "ITER_DYN", "STATUS_DYN", "STATUS_SS"):
+            lin["%s_%s" % (tag, key)] = rec[key]
+    np.savez_compressed(os.path.join(HERE, "lmpc_oracle.npz"), **lin)
     print("wrote fixtures")
 
 

@@ -131,3 +131,31 @@ def test_closed_loop_of_device_code_matches_oracle_fixture(nmpc):
     for key in ("U", "X_HAT", "D_HAT", "XS", "US", "Xp", "Yp"):
         assert np.abs(rec[key] - G["cl_" + key]).max() < 1e-6, key
     assert np.all(np.abs(rec["F_DYN"] - G["cl_F_DYN"]) <= 1e-8 * np.maximum(1.0, np.abs(G["cl_F_DYN"])))
+
+
+L = np.load(os.path.join(GOLDEN, "lmpc_oracle.npz"))
+
+
+def _check_linear_loop(bundle, tag):
+    from harness_loop import HarnessLoop
+    Ns = L[tag + "_U"].shape[0]
+    rec = HarnessLoop(bundle, 1).run(Ns)
+    assert np.array_equal(rec["STATUS_DYN"][:, 0], L[tag + "_STATUS_DYN"])
+    assert np.array_equal(rec["ITER_DYN"][:, 0], L[tag + "_ITER_DYN"])
+    for key in ("U", "X_HAT", "D_HAT", "XS", "US", "Xp", "Yp"):
+        assert np.abs(rec[key][:, 0, :] - L["%s_%s" % (tag, key)]).max() < 1e-6, key
+    ok = L[tag + "_STATUS_DYN"] == 0
+    assert np.all(np.abs(rec["F_DYN"][ok, 0] - L[tag + "_F_DYN"][ok]) <= 1e-8 * np.maximum(1.0, np.abs(L[tag + "_F_DYN"][ok])))
+
+
+def test_lmpc_cstr_closed_loop_including_infeasible_first_steps(lmpc_cstr):
+    """BASELINE configs[0].  The shipped initial state makes x_1 <= xmax unreachable: the first OCPs are infeasible
+    and the loop keeps u = u0 (MPC_code.py:804-805) until the state has decayed."""
+    assert list(L["cstr_STATUS_DYN"][:4]) == [2, 2, 2, 0]
+    _check_linear_loop(lmpc_cstr, "cstr")
+
+
+def test_lmpc_wb_closed_loop_with_delta_u_cost(lmpc_wb):
+    """BASELINE configs[2]: Delta-u penalty (DUForm) - the device carries u_{k-1} as extra stage state."""
+    assert lmpc_wb.ocp.uses_uprev and lmpc_wb.prob.flags["DUForm"] is True
+    _check_linear_loop(lmpc_wb, "wb")

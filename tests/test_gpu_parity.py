@@ -156,3 +156,44 @@ def test_full_size_batch_properties(nmpc, cp):
         lb, ub = nmpc.ocp.w_lb.copy(), nmpc.ocp.w_ub.copy(); lb[:n] = ub[:n] = xh[i]
         r = on.solve(w0[i], par[i], lb, ub, opts=IpmOptions(max_iter=100))
         assert r.status == 0 and np.abs(r.x - wn[i]).max() < U_TOL
+
+
+L = np.load(os.path.join(GOLDEN, "lmpc_oracle.npz"))
+
+
+@pytest.mark.parametrize("name,tag", [("lmpc_cstr", "cstr"), ("lmpc_wb", "wb")])
+def test_linear_configs_closed_loop_match_oracle(name, tag, request):
+    """Ex_LMPC_CSTR (Kalman filter, infeasible first steps) and Ex_LMPC_WB (Luenberger observer, Delta-u cost):
+    a batch of identical instances must reproduce the single-instance oracle trajectory."""
+    from mpc_code_b200.mpc_loop import CompiledProblem
+    bundle = request.getfixturevalue(name)
+    B, Ns = 5, L[tag + "_U"].shape[0]
+    ctl = CompiledProblem(bundle.prob, name).controller(B)
+    rec = ctl.run(Ns)
+    st = rec["STATUS_DYN"].cpu().numpy()
+    assert np.all(st == L[tag + "_STATUS_DYN"][:, None])
+    assert np.all(rec["ITER_DYN"].cpu().numpy() == L[tag + "_ITER_DYN"][:, None])
+    for key in ("U", "X_HAT", "D_HAT", "XS", "US", "Xp", "Yp"):
+        diff = np.abs(rec[key].cpu().numpy() - L["%s_%s" % (tag, key)][:, None, :]).max()
+        assert diff < U_TOL, (key, diff)
+    ok = L[tag + "_STATUS_DYN"] == 0
+    fd = np.abs(rec["F_DYN"].cpu().numpy()[ok] - L[tag + "_F_DYN"][ok][:, None])
+    assert np.all(fd <= F_RTOL * np.maximum(1.0, np.abs(L[tag + "_F_DYN"][ok][:, None])))
+
+
+def test_wood_berry_full_batch(lmpc_wb):
+    """BASELINE configs[2] at its full size (16 384 instances, perturbed initial states): all solved, instances independent."""
+    from mpc_code_b200.mpc_loop import CompiledProblem
+    p = lmpc_wb.prob
+    B = 16384
+    x0 = 0.1 * np.random.default_rng(3).uniform(-1, 1, (B, p.nx))
+    ctl = CompiledProblem(p, "lmpc_wb").controller(B)
+    ctl.reset(x0_p=x0, x0_m=x0)
+    rec = ctl.run(14)
+    assert int((rec["STATUS_DYN"] != 0).sum()) == 0
+    u = rec["U"].cpu().numpy()
+    assert np.all(np.abs(u) <= 0.5 + 1e-7)
+    ctl2 = CompiledProblem(p, "lmpc_wb").controller(64)
+    ctl2.reset(x0_p=x0[100:164], x0_m=x0[100:164])
+    u2 = ctl2.run(14)["U"].cpu().numpy()
+    assert np.array_equal(u[:, 100:164, :], u2)
