@@ -196,7 +196,7 @@ def run_gpu(args):
     ctl.reset(x0_p=x0, x0_m=x0)
     ys, us, stat = [], [], []
     for k in range(W):
-        o = ctl.step(noise_dev[k]); ys.append(o["Yp"]); us.append(o["U"])
+        o = ctl.step_fused(noise_dev[k]); ys.append(o["Yp"]); us.append(o["U"].clone())
     clock_file = os.path.join(tempfile.gettempdir(), "mpcb_clocks_%d.csv" % os.getpid())
     sampler = _clock_sampler(clock_file) if rank == 0 else None
     ctl.h.set_profiling(True)
@@ -205,9 +205,9 @@ def run_gpu(args):
     barrier()
     ev[0].record()
     for k in range(K):
-        o = ctl.step(noise_dev[W + k])
+        o = ctl.step_fused(noise_dev[W + k])
         ev[k + 1].record()
-        ys.append(o["Yp"]); us.append(o["U"]); stat.append((o["STATUS_DYN"], o["ITER_DYN"], o["STATUS_SS"]))
+        ys.append(o["Yp"]); us.append(o["U"].clone()); stat.append((o["STATUS_DYN"].clone(), o["ITER_DYN"].clone(), o["STATUS_SS"].clone()))
     barrier()
     elapsed_ms = ev[0].elapsed_time(ev[K])
     prof = ctl.h.profile()
@@ -228,13 +228,13 @@ def run_gpu(args):
     y_dev = torch.empty(B, prob.ny, device=dev, dtype=torch.float64)
     ctl.reset(x0_p=x0, x0_m=x0)
     for k in range(W):
-        y_dev.copy_(y_host[k], non_blocking=True); o = ctl.step(y_meas=y_dev); u_host[k].copy_(o["U"], non_blocking=True)
+        y_dev.copy_(y_host[k], non_blocking=True); o = ctl.step_fused(y_meas=y_dev); u_host[k].copy_(o["U"], non_blocking=True)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for k in range(W, total):
         y_dev.copy_(y_host[k], non_blocking=True)                    # H2D of this step's measurement
-        o = ctl.step(y_meas=y_dev)
+        o = ctl.step_fused(y_meas=y_dev)
         u_host[k].copy_(o["U"], non_blocking=True)                   # D2H of the computed inputs
         torch.cuda.current_stream(dev).synchronize()                 # the caller needs u_k before the next sample
     e1.record()

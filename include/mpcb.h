@@ -118,6 +118,22 @@ int  mpcb_model_step(mpcb_handle_t h, const double* x, const double* u, const do
 int  mpcb_stage_derivs(mpcb_handle_t h, const double* par, const double* w, const double* lam,
                        double* A, double* Bm, double* c, double* H, void* stream);
 
+/* Fused closed-loop step (the throughput entry point): estimator -> target -> OCP -> extraction with the loop state
+ * (x_hat, d_hat, P, u_{k-1}, targets, warm start) kept on the device between calls, i.e. MPC_code.py:546-805 for
+ * every instance without host glue.
+ *   mpcb_loop_reset: initial loop state (MPC_code.py:442-463); x0_m [B,nx], u0 [B,nu], dhat0 [B,nd] or NULL, P0 [B,nxi*nxi] or NULL.
+ *   mpcb_step: y_meas [B,ny] measurement; t [B]; sp [B, nu+ny+nx] = usp|ysp|xsp (defSP, MPC_code.py:679);
+ *              px [B,npx*N], py [B,npy*N] horizon parameters (MPC_code.py:492-501) or NULL for zeros;
+ *              outputs u_out [B,nu] (input to apply), xhat_out [B,nx] / dhat_out [B,nd] (x(k|k), d(k|k)),
+ *              xs_out / us_out (targets), f_dyn, status_dyn, iters_dyn, status_ss [B].
+ *   mpcb_loop_get: copies the kept state (xi = [x(k+1|k); d] [B,nxi], P [B,nxi*nxi], u [B,nu]; any may be NULL) out.
+ */
+int  mpcb_loop_reset(mpcb_handle_t h, const double* x0_m, const double* u0, const double* dhat0, const double* P0);
+int  mpcb_step(mpcb_handle_t h, int est_type, const double* y_meas, const double* t, const double* sp, const double* px,
+               const double* py, double* u_out, double* xhat_out, double* dhat_out, double* xs_out, double* us_out,
+               double* f_dyn, int* status_dyn, int* iters_dyn, int* status_ss, void* stream);
+int  mpcb_loop_get(mpcb_handle_t h, double* xi, double* P, double* u, void* stream);
+
 /* Profiling.  With profiling on, every kernel launch is bracketed by CUDA events on its stream and the
  * time is accumulated per kernel class: 0 ocp_init, 1 ocp_eval (stage derivatives), 2 ocp_kkt (Riccati
  * step), 3 ocp_trial (line-search evaluation), 4 ocp_accept, 5 target, 6 estimate, 7 other.

@@ -198,6 +198,118 @@ __global__ void k_plant_step(int B, double* x, const double* u, const double* t,
 }
 #endif
 
+
+#if MPCB_HAS_OCP && MPCB_HAS_TARGET
+// ---------------------------------------------------------------------------------------------
+// Loop glue of one closed-loop step as device kernels (mpcb_step): the statements of MPC_code.py:655-700,
+// 714-718, 734-772 and 786-805 for every instance.
+// ---------------------------------------------------------------------------------------------
+struct LoopState {      // per-instance loop state kept on the device between steps (MPC_code.py:442-463)
+    double *xi, *P, *u, *us, *xs, *wguess, *wopt, *x0m, *u0, *parss, *wss, *par, *w, *px0, *py0, *fss;
+    int *dyn_status, *ss_status, *ss_iters;
+};
+
+__global__ void k_step_params(int B, const double* px, const double* py, LoopState L) {
+    const int inst = blockIdx.x * blockDim.x + threadIdx.x;
+    if (inst >= B) return;
+    for (int i = 0; i < NPX; ++i) L.px0[(size_t)inst * NPX + i] = px ? px[(size_t)inst * NPX * NH + i] : 0.0;
+    for (int i = 0; i < NPY; ++i) L.py0[(size_t)inst * NPY + i] = py ? py[(size_t)inst * NPY * NH + i] : 0.0;
+}
+
+// after the estimator: outputs, par_ss (Target_Calc.py:41-50 order, MPC_code.py:693) and the target guess (:696-700)
+__global__ void k_step_pre(int B, const double* t, const double* sp, LoopState L, double* xhat_out, double* dhat_out) {
+    const int inst = blockIdx.x * blockDim.x + threadIdx.x;
+    if (inst >= B) return;
+    const double* xi = L.xi + (size_t)inst * NXI;
+    double* ps = L.parss + (size_t)inst * MPCB_NPARSS;
+    for (int i = 0; i < NX; ++i) xhat_out[(size_t)inst * NX + i] = xi[i];
+    double d[ND + 1];
+    for (int i = 0; i < ND; ++i) { d[i] = (NXI > NX) ? xi[NX + i] : 0.0; dhat_out[(size_t)inst * ND + i] = d[i]; }
+    const double* spi = sp + (size_t)inst * (NU + NY + NX);
+    for (int i = 0; i < NU; ++i) ps[MPCB_OFFSS_USP + i] = spi[i];
+    for (int i = 0; i < NY; ++i) ps[MPCB_OFFSS_YSP + i] = spi[NU + i];
+    for (int i = 0; i < NX; ++i) ps[MPCB_OFFSS_XSP + i] = spi[NU + NY + i];
+    for (int i = 0; i < ND; ++i) ps[MPCB_OFFSS_D + i] = d[i];
+    for (int i = 0; i < NU; ++i) ps[MPCB_OFFSS_USPREV + i] = L.us[(size_t)inst * NU + i];
+    for (int i = 0; i < NY * NU; ++i) ps[MPCB_OFFSS_LAM + i] = 0.0;
+    ps[MPCB_OFFSS_T] = t[inst];
+    double py[NPY + 1];
+    for (int i = 0; i < NPX; ++i) ps[MPCB_OFFSS_PX + i] = L.px0[(size_t)inst * NPX + i];
+    for (int i = 0; i < NPY; ++i) { py[i] = L.py0[(size_t)inst * NPY + i]; ps[MPCB_OFFSS_PY + i] = py[i]; }
+    double* wg = L.wss + (size_t)inst * NWS;
+    double x0[NX], u0[NU], y0[NY], tt = t[inst];
+    for (int i = 0; i < NX; ++i) { x0[i] = L.x0m[(size_t)inst * NX + i]; wg[i] = x0[i]; }
+    for (int i = 0; i < NU; ++i) { u0[i] = L.u0[(size_t)inst * NU + i]; wg[NX + i] = u0[i]; }
+    mdl_fy(x0, u0, d, &tt, py, y0);
+    for (int i = 0; i < NY; ++i) wg[NZ + i] = y0[i];
+}
+
+// after the target solve: status gate (:714-718), par (Control_Calc.py:43-57 order, MPC_code.py:769-772), warm start (:740-764)
+__global__ void k_step_mid(int B, int first, const double* t, const double* px, const double* py, LoopState L,
+                           double* xs_out, double* us_out) {
+    const int inst = blockIdx.x * blockDim.x + threadIdx.x;
+    if (inst >= B) return;
+    double* xs = L.xs + (size_t)inst * NX; double* us = L.us + (size_t)inst * NU;
+    const double* wss = L.wss + (size_t)inst * NWS;
+    double xs_prev[NX], us_prev[NU];
+    for (int i = 0; i < NX; ++i) xs_prev[i] = xs[i];
+    for (int i = 0; i < NU; ++i) us_prev[i] = us[i];
+    if (L.ss_status[inst] != 2) {
+        for (int i = 0; i < NX; ++i) xs[i] = wss[i];
+        for (int i = 0; i < NU; ++i) us[i] = wss[NX + i];
+    }
+    for (int i = 0; i < NX; ++i) xs_out[(size_t)inst * NX + i] = xs[i];
+    for (int i = 0; i < NU; ++i) us_out[(size_t)inst * NU + i] = us[i];
+    const double* xi = L.xi + (size_t)inst * NXI;
+    double* pr = L.par + (size_t)inst * NPAR;
+    for (int i = 0; i < NX; ++i) { pr[MPCB_OFF_X0 + i] = xi[i]; pr[MPCB_OFF_XS + i] = xs[i]; }
+    for (int i = 0; i < NU; ++i) { pr[MPCB_OFF_US + i] = us[i]; pr[MPCB_OFF_UM1 + i] = L.u[(size_t)inst * NU + i]; }
+    for (int i = 0; i < ND; ++i) pr[MPCB_OFF_D + i] = (NXI > NX) ? xi[NX + i] : 0.0;
+    pr[MPCB_OFF_T] = t[inst];
+    for (int i = 0; i < NY * NU; ++i) pr[MPCB_OFF_LAM + i] = 0.0;
+    for (int i = 0; i < NPX * NH; ++i) pr[MPCB_OFF_PX + i] = px ? px[(size_t)inst * NPX * NH + i] : 0.0;
+    for (int i = 0; i < NPY * NH; ++i) pr[MPCB_OFF_PY + i] = py ? py[(size_t)inst * NPY * NH + i] : 0.0;
+    double* wg = L.wguess + (size_t)inst * NW; double* w = L.w + (size_t)inst * NW;
+    if (first) {
+        for (int k = 0; k <= NH; ++k) {
+            for (int i = 0; i < NX; ++i) wg[k * NZ + i] = L.x0m[(size_t)inst * NX + i];
+            if (k < NH) for (int i = 0; i < NU; ++i) wg[k * NZ + NX + i] = L.u0[(size_t)inst * NU + i];
+        }
+    } else if (L.dyn_status[inst] != 2) {
+        const double* wo = L.wopt + (size_t)inst * NW;
+        for (int i = 0; i < NW - NZ; ++i) wg[i] = wo[NZ + i];
+        for (int i = 0; i < NU; ++i) wg[NW - NZ + i] = us_prev[i];
+        for (int i = 0; i < NX; ++i) wg[NW - NX + i] = xs_prev[i];
+    }
+    for (int i = 0; i < NW; ++i) w[i] = wg[i];
+}
+
+// after the OCP: status gate, u_k and x(k+1|k) extraction or model fallback (:786-805)
+__global__ void k_step_post(int B, const double* t, const int* status, LoopState L, double* u_out) {
+    const int inst = blockIdx.x * blockDim.x + threadIdx.x;
+    if (inst >= B) return;
+    double* xi = L.xi + (size_t)inst * NXI; double* u = L.u + (size_t)inst * NU;
+    const double* w = L.w + (size_t)inst * NW;
+    const int st = status[inst];
+    L.dyn_status[inst] = st;
+    if (st != 2) {
+        double* wo = L.wopt + (size_t)inst * NW;
+        for (int i = 0; i < NW; ++i) wo[i] = w[i];
+        for (int i = 0; i < NU; ++i) u[i] = w[NX + i];
+        for (int i = 0; i < NX; ++i) xi[i] = w[NZ + i];
+    } else {
+        double x[NX], ul[NU], d[ND + 1], pxl[NPX + 1], xn[NX];
+        for (int i = 0; i < NX; ++i) x[i] = xi[i];
+        for (int i = 0; i < NU; ++i) ul[i] = u[i];
+        for (int i = 0; i < ND; ++i) d[i] = (NXI > NX) ? xi[NX + i] : 0.0;
+        for (int i = 0; i < NPX; ++i) pxl[i] = L.px0[(size_t)inst * NPX + i];
+        dyn_value(x, ul, d, pxl, t[inst], xn);
+        for (int i = 0; i < NX; ++i) xi[i] = xn[i];
+    }
+    for (int i = 0; i < NU; ++i) u_out[(size_t)inst * NU + i] = u[i];
+}
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -209,6 +321,11 @@ struct mpcb_ctx {
     InstState* st;
     int* n_active; int* h_active;
     int have_dbounds, last_launches, last_ticks;
+    // loop state of the fused step (mpcb_loop_reset / mpcb_step)
+    double* loop_mem; int* loop_imem; int loop_first;
+#if MPCB_HAS_OCP && MPCB_HAS_TARGET
+    LoopState L;
+#endif
     // profiling (mpcb_set_profiling): CUDA-event time and launch count per kernel class
     int profile;
     unsigned long long* counters;
@@ -325,6 +442,7 @@ int mpcb_create(int batch, const mpcb_opts_t* oss, const mpcb_opts_t* odyn, mpcb
     CK(cudaMallocHost(&h->h_active, sizeof(int)));
     CK(cudaMalloc(&h->counters, 2 * sizeof(unsigned long long)));
     CK(cudaMemset(h->counters, 0, 2 * sizeof(unsigned long long)));
+    h->loop_mem = nullptr; h->loop_imem = nullptr; h->loop_first = 1;
     h->profile = 0; h->eval_instances = h->trial_instances = 0;
     for (int i = 0; i < MPCB_NKERNELS; ++i) { h->kernel_ms[i] = 0.0; h->kernel_launches[i] = 0; }
     return 0;
@@ -336,6 +454,7 @@ int mpcb_destroy(mpcb_handle_t h) {
     cudaFree(h->ss_lbx); cudaFree(h->ss_ubx); cudaFree(h->Qkf); cudaFree(h->Rkf); cudaFree(h->Kest);
     cudaFree(h->dmin); cudaFree(h->dmax); cudaFree(h->n_active); cudaFreeHost(h->h_active); cudaFree(h->counters);
     for (auto e : h->ev_pool) cudaEventDestroy(e);
+    cudaFree(h->loop_mem); cudaFree(h->loop_imem);
     delete h;
     return 0;
 }
@@ -530,6 +649,85 @@ int mpcb_dfma_peak(int iters, double* tflops) {
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
     *tflops = best;
     return 0;
+}
+
+int mpcb_loop_reset(mpcb_handle_t h, const double* x0_m, const double* u0, const double* dhat0, const double* P0) {
+#if MPCB_HAS_OCP && MPCB_HAS_TARGET
+    const size_t B = (size_t)h->B;
+    if (!h->loop_mem) {
+        const size_t n = B * (NXI + NXI * NXI + 3 * NU + 2 * NX + 3 * NW + MPCB_NPARSS + NWS + NPAR + NPX + NPY + 1);
+        CK(cudaMalloc(&h->loop_mem, sizeof(double) * n));
+        CK(cudaMalloc(&h->loop_imem, sizeof(int) * 3 * B));
+        double* p = h->loop_mem;
+        LoopState& L = h->L;
+        L.xi = p; p += B * NXI; L.P = p; p += B * NXI * NXI; L.u = p; p += B * NU; L.us = p; p += B * NU; L.u0 = p; p += B * NU;
+        L.xs = p; p += B * NX; L.x0m = p; p += B * NX; L.wguess = p; p += B * NW; L.wopt = p; p += B * NW; L.w = p; p += B * NW;
+        L.parss = p; p += B * MPCB_NPARSS; L.wss = p; p += B * NWS; L.par = p; p += B * NPAR; L.px0 = p; p += B * NPX;
+        L.py0 = p; p += B * NPY; L.fss = p; p += B;
+        L.dyn_status = h->loop_imem; L.ss_status = h->loop_imem + B; L.ss_iters = h->loop_imem + 2 * B;
+    }
+    LoopState& L = h->L;
+    CK(cudaMemset(h->loop_mem, 0, sizeof(double) * B * (NXI + NXI * NXI)));
+    CK(cudaMemset(h->loop_imem, 0, sizeof(int) * 3 * B));
+    CK(cudaMemcpy2D(L.xi, sizeof(double) * NXI, x0_m, sizeof(double) * NX, sizeof(double) * NX, B, cudaMemcpyDeviceToDevice));
+    if (NXI > NX && dhat0)
+        CK(cudaMemcpy2D(L.xi + NX, sizeof(double) * NXI, dhat0, sizeof(double) * ND, sizeof(double) * ND, B, cudaMemcpyDeviceToDevice));
+    if (P0) CK(cudaMemcpy(L.P, P0, sizeof(double) * B * NXI * NXI, cudaMemcpyDeviceToDevice));
+    CK(cudaMemcpy(L.x0m, x0_m, sizeof(double) * B * NX, cudaMemcpyDeviceToDevice));
+    CK(cudaMemcpy(L.xs, x0_m, sizeof(double) * B * NX, cudaMemcpyDeviceToDevice));            // MPC_code.py:682-684
+    CK(cudaMemcpy(L.u0, u0, sizeof(double) * B * NU, cudaMemcpyDeviceToDevice));
+    CK(cudaMemcpy(L.u, u0, sizeof(double) * B * NU, cudaMemcpyDeviceToDevice));
+    CK(cudaMemcpy(L.us, u0, sizeof(double) * B * NU, cudaMemcpyDeviceToDevice));
+    h->loop_first = 1;
+    return 0;
+#else
+    h->err = "library built without OCP/target"; return -3;
+#endif
+}
+
+int mpcb_loop_get(mpcb_handle_t h, double* xi, double* P, double* u, void* stream) {
+#if MPCB_HAS_OCP && MPCB_HAS_TARGET
+    if (!h->loop_mem) { h->err = "mpcb_loop_reset has not been called"; return -2; }
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t B = (size_t)h->B;
+    if (xi) CK(cudaMemcpyAsync(xi, h->L.xi, sizeof(double) * B * NXI, cudaMemcpyDeviceToDevice, s));
+    if (P) CK(cudaMemcpyAsync(P, h->L.P, sizeof(double) * B * NXI * NXI, cudaMemcpyDeviceToDevice, s));
+    if (u) CK(cudaMemcpyAsync(u, h->L.u, sizeof(double) * B * NU, cudaMemcpyDeviceToDevice, s));
+    return 0;
+#else
+    h->err = "library built without OCP/target"; return -3;
+#endif
+}
+
+int mpcb_step(mpcb_handle_t h, int est_type, const double* y_meas, const double* t, const double* sp, const double* px,
+              const double* py, double* u_out, double* xhat_out, double* dhat_out, double* xs_out, double* us_out,
+              double* f_dyn, int* status_dyn, int* iters_dyn, int* status_ss, void* stream) {
+#if MPCB_HAS_OCP && MPCB_HAS_TARGET
+    if (!h->loop_mem) { h->err = "mpcb_loop_reset has not been called"; return -2; }
+    cudaStream_t s = (cudaStream_t)stream;
+    LoopState& L = h->L;
+    const int B = h->B, g = nblk(B, 128);
+    int launches = 0;
+    k_step_params<<<g, 128, 0, s>>>(B, px, py, L); launches++;
+    int rc = mpcb_estimate(h, est_type, y_meas, L.u, t, L.px0, L.py0, L.xi, L.P, s); launches++;
+    if (rc) return rc;
+    k_step_pre<<<g, 128, 0, s>>>(B, t, sp, L, xhat_out, dhat_out); launches++;
+    rc = mpcb_target(h, L.parss, L.wss, L.fss, L.ss_status, L.ss_iters, s); launches++;
+    if (rc) return rc;
+    k_step_mid<<<g, 128, 0, s>>>(B, h->loop_first, t, px, py, L, xs_out, us_out); launches++;
+    rc = mpcb_ocp(h, L.par, L.w, f_dyn, status_dyn, iters_dyn, s);
+    if (rc) return rc;
+    launches += h->last_launches;
+    k_step_post<<<g, 128, 0, s>>>(B, t, status_dyn, L, u_out); launches++;
+    if (status_ss) CK(cudaMemcpyAsync(status_ss, L.ss_status, sizeof(int) * B, cudaMemcpyDeviceToDevice, s));
+    CK(cudaGetLastError());
+    h->kernel_launches[KC_OTHER] += 4;
+    h->loop_first = 0;
+    h->last_launches = launches;
+    return 0;
+#else
+    h->err = "library built without OCP/target"; return -3;
+#endif
 }
 
 int mpcb_last_launches(mpcb_handle_t h) { return h->last_launches; }

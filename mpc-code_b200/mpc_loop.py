@@ -94,6 +94,7 @@ class BatchedMpc:
         self.w_opt = None; self.w_guess = None
         self.dyn_status = t.zeros(self.B, dtype=t.int32, device=self.h.device)
         self.dead = t.zeros(self.B, dtype=t.bool, device=self.h.device)
+        self._fused = False
         self.x_k0, self.dhat0, self.P0 = self.x_k.clone(), self.dhat_k.clone(), self.P_k.clone()
         self.ksim = 0
 
@@ -230,13 +231,66 @@ class BatchedMpc:
         self.ksim += 1
         return out
 
-    def run(self, Nsim: Optional[int] = None, noise=None, state_noise=None) -> Dict[str, object]:
+    # -- the same step through the fused C entry point (mpcb_step): no host glue between the solves ----------
+    def fused_reset(self):
+        """Hand the current loop state to the device-resident loop of `mpcb_step`."""
+        self.solver_ss._push_bounds(None, None, None, None)      # w_lb/w_ub/g_lb/g_ub of the builders -> device constants
+        self.solver._push_bounds(None, None, None, None)
+        self.h.loop_reset(self.xhat_k, self.u_k, self.dhat_k if self.prob.nd else None, self.P_k)
+        self._fused = True
+
+    def step_fused(self, noise=None, y_meas=None) -> Dict[str, object]:
+        """One closed-loop step with estimator, target, OCP and extraction done by `mpcb_step`.  Same semantics and
+        results as `step` (tests compare them); only the plant simulation and the set-point lookup stay on the host."""
+        if not getattr(self, "_fused", False):
+            self.fused_reset()
+        p, t, h = self.prob, self.torch, self.h
+        B, dev, f64 = self.B, h.device, t.float64
+        t_k = self.ksim * p.h
+        if getattr(self, "_tt", None) is None:
+            self._tt = t.empty(B, 1, device=dev, dtype=f64)
+        self._tt.fill_(t_k)
+        tt = self._tt
+        p_xk, p_yk, p_xmp, p_ymp, p_xp, p_yp = self._params(t_k)
+        row = lambda v: t.as_tensor(np.asarray(v, dtype=float).reshape(1, -1), device=dev).expand(B, -1).contiguous()  # noqa: E731
+        varying = any(k in p.ns for k in ("def_px", "def_py"))
+        px = row(p_xk.reshape(-1, order="F")) if varying else None
+        py = row(p_yk.reshape(-1, order="F")) if varying else None
+        out: Dict[str, object] = {}
+        if y_meas is None:
+            out["Xp"] = self.x_k.clone()
+            if p.flags["Fp_nominal"] is True:
+                raise NotImplementedError("fused step with a nominal plant: pass y_meas")
+            y_meas = h.plant_meas(self.x_k, self.u_k, tt, row(p_yp), row(p_ymp), noise)
+            simulate = True
+        else:
+            simulate = False
+        out["Yp"] = y_meas
+        sp_key = t_k if p.defSP is not None else None
+        if getattr(self, "_sp_key", object()) != sp_key or getattr(self, "_sp", None) is None:
+            vals = p.defSP(t_k) if p.defSP is not None else (np.zeros(p.ny), np.zeros(p.nu), np.zeros(p.nx))
+            ysp, usp, xsp = [np.asarray(v, dtype=float).ravel() for v in vals]
+            self._sp = row(np.concatenate([usp, ysp, xsp])); self._sp_key = sp_key
+        o = h.step(self.est_type, y_meas, tt, self._sp, px, py)
+        self.u_k = o["u"]
+        out.update(U=o["u"], X_CORR=o["xhat"], D_HAT=o["dhat"], XS=o["xs"], US=o["us"], F_DYN=o["f"],
+                   STATUS_DYN=o["status"], ITER_DYN=o["iters"], STATUS_SS=o["status_ss"])
+        if simulate:
+            self.x_k = h.plant_step(self.x_k, self.u_k, tt, row(p_xp), row(p_xmp))
+        self.ksim += 1
+        return out
+
+    def run(self, Nsim: Optional[int] = None, noise=None, state_noise=None, fused: bool = False) -> Dict[str, object]:
         """Run ``Nsim`` steps and stack the per-step records into ``[Nsim, B, n]`` tensors (``MPC_code.py:877-895``)."""
         t = self.torch
         Nsim = self.prob.Nsim if Nsim is None else Nsim
         rec: Dict[str, list] = {}
         for k in range(Nsim):
-            o = self.step(None if noise is None else noise[k], None if state_noise is None else state_noise[k])
+            if fused:
+                o = {key: (val.clone() if isinstance(val, t.Tensor) else val)
+                     for key, val in self.step_fused(None if noise is None else noise[k]).items()}
+            else:
+                o = self.step(None if noise is None else noise[k], None if state_noise is None else state_noise[k])
             for key, val in o.items():
                 rec.setdefault(key, []).append(val)
         return {k: t.stack([t.as_tensor(x) for x in v]) for k, v in rec.items()}

@@ -34,7 +34,8 @@ class MpcbOpts(ctypes.Structure):
 C_SYMBOLS = ("mpcb_abi_version", "mpcb_default_opts", "mpcb_get_dims", "mpcb_model_flops", "mpcb_create",
              "mpcb_destroy", "mpcb_last_error", "mpcb_set_const", "mpcb_estimate", "mpcb_target", "mpcb_ocp",
              "mpcb_plant_meas", "mpcb_plant_step", "mpcb_model_output", "mpcb_model_step", "mpcb_stage_derivs",
-             "mpcb_last_launches", "mpcb_last_ticks", "mpcb_set_profiling", "mpcb_get_profile", "mpcb_dfma_peak")
+             "mpcb_last_launches", "mpcb_last_ticks", "mpcb_set_profiling", "mpcb_get_profile", "mpcb_dfma_peak",
+             "mpcb_loop_reset", "mpcb_step", "mpcb_loop_get")
 
 
 class MpcbLibrary:
@@ -68,6 +69,9 @@ class MpcbLibrary:
         L.mpcb_get_profile.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_long),
                                        ctypes.POINTER(ctypes.c_ulonglong)]
         L.mpcb_dfma_peak.argtypes = [ci, ctypes.POINTER(ctypes.c_double)]
+        L.mpcb_loop_reset.argtypes = [vp] * 5
+        L.mpcb_step.argtypes = [vp, ci] + [vp] * 15
+        L.mpcb_loop_get.argtypes = [vp] * 5
         self.dims = MpcbDims()
         L.mpcb_get_dims(ctypes.byref(self.dims))
 
@@ -226,6 +230,44 @@ class MpcbHandle:
                                              c.data_ptr(), H.data_ptr(), self._stream()))
         self.launches += 1
         return A, Bm, c, H
+
+    # -- fused closed-loop step ---------------------------------------------------
+    def loop_reset(self, x0_m, u0, dhat0=None, P0=None):
+        d = self.lib.dims
+        x0_m = self.tensor(x0_m, d.nx); u0 = self.tensor(u0, d.nu)
+        dh = self.tensor(dhat0, d.nd) if (dhat0 is not None and d.nd) else None
+        P0 = self.tensor(P0, d.nxi * d.nxi) if P0 is not None else None
+        _torch().cuda.current_stream(self.device).synchronize()
+        self._check(self.L.mpcb_loop_reset(self._h, x0_m.data_ptr(), u0.data_ptr(), dh.data_ptr() if dh is not None else None,
+                                           P0.data_ptr() if P0 is not None else None))
+        torch = _torch()
+        B = self.batch
+        self._step_out = dict(u=self.empty(B, d.nu), xhat=self.empty(B, d.nx), dhat=self.empty(B, max(d.nd, 1)),
+                              xs=self.empty(B, d.nx), us=self.empty(B, d.nu), f=self.empty(B),
+                              status=self.empty(B, dtype=torch.int32), iters=self.empty(B, dtype=torch.int32),
+                              status_ss=self.empty(B, dtype=torch.int32))
+
+    def step(self, est_type, y_meas, t, sp, px=None, py=None):
+        """One fused step; returns the dict of output tensors (reused between calls - clone to keep)."""
+        d = self.lib.dims
+        y = self.tensor(y_meas, d.ny); t = self.tensor(t, 1); sp = self.tensor(sp, d.nu + d.ny + d.nx)
+        px = self.tensor(px, d.npx * d.N) if px is not None else None
+        py = self.tensor(py, d.npy * d.N) if py is not None else None
+        o = self._step_out
+        self._check(self.L.mpcb_step(self._h, int(est_type), y.data_ptr(), t.data_ptr(), sp.data_ptr(),
+                                     px.data_ptr() if px is not None else None, py.data_ptr() if py is not None else None,
+                                     o["u"].data_ptr(), o["xhat"].data_ptr(), o["dhat"].data_ptr(), o["xs"].data_ptr(),
+                                     o["us"].data_ptr(), o["f"].data_ptr(), o["status"].data_ptr(), o["iters"].data_ptr(),
+                                     o["status_ss"].data_ptr(), self._stream()))
+        self.launches += self.L.mpcb_last_launches(self._h)
+        return o
+
+    def loop_state(self):
+        """Copies of the device-resident loop state: xi = [x(k+1|k); d], P, u."""
+        d = self.lib.dims
+        xi, P, u = self.empty(self.batch, d.nxi), self.empty(self.batch, d.nxi * d.nxi), self.empty(self.batch, d.nu)
+        self._check(self.L.mpcb_loop_get(self._h, xi.data_ptr(), P.data_ptr(), u.data_ptr(), self._stream()))
+        return xi, P, u
 
     @property
     def last_ticks(self):

@@ -197,3 +197,23 @@ def test_wood_berry_full_batch(lmpc_wb):
     ctl2.reset(x0_p=x0[100:164], x0_m=x0[100:164])
     u2 = ctl2.run(14)["U"].cpu().numpy()
     assert np.array_equal(u[:, 100:164, :], u2)
+
+
+@pytest.mark.parametrize("name,fixture", [("nmpc_cstr", "nmpc"), ("lmpc_cstr", "lmpc_cstr"), ("lmpc_wb", "lmpc_wb")])
+def test_fused_step_equals_the_python_loop(name, fixture, request):
+    """`mpcb_step` (device-resident loop state, glue kernels) against the statement-by-statement loop of mpc_loop.py."""
+    from mpc_code_b200.mpc_loop import CompiledProblem
+    bundle = request.getfixturevalue(fixture)
+    p = bundle.prob
+    cp_ = CompiledProblem(p, name)
+    B, Ns = 6, 10
+    rng = np.random.default_rng(11)
+    scale = np.array([0.01, 0.001, 0.01]) if name == "nmpc_cstr" else 0.01      # keep the CSTR level away from its bound (D7)
+    x0 = np.tile(p.x0_p, (B, 1)) * (1 + scale * rng.uniform(-1, 1, (B, p.nxp))) + 0.01 * rng.uniform(-1, 1, (B, p.nxp)) * (name == "lmpc_wb")
+    noise = 3e-4 * rng.standard_normal((Ns, B, p.ny)) if p.R_wn is not None else None
+    a = cp_.controller(B); a.reset(x0_p=x0, x0_m=x0); ra = a.run(Ns, noise=noise)
+    b = cp_.controller(B); b.reset(x0_p=x0, x0_m=x0); rb = b.run(Ns, noise=noise, fused=True)
+    assert np.array_equal(ra["STATUS_DYN"].cpu().numpy(), rb["STATUS_DYN"].cpu().numpy())
+    assert np.array_equal(ra["ITER_DYN"].cpu().numpy(), rb["ITER_DYN"].cpu().numpy())
+    for key in ("U", "XS", "US", "D_HAT", "Xp", "Yp", "F_DYN"):
+        assert (ra[key] - rb[key]).abs().max().item() == 0.0, key
