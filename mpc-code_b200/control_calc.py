@@ -38,6 +38,7 @@ class OcpSpec:
     sol_opts: Dict[str, Any] = field(default_factory=dict)
     quad_cost: Optional[SX] = None      # ContForm: integrand of the stage cost     (:102-111)
     cont_rhs: Optional[SX] = None       # ContForm: ode right-hand side fx(...)+px  (:103)
+    cont_substeps: int = 0
 
     @property
     def uses_uprev(self) -> bool:
@@ -100,11 +101,20 @@ def build_ocp_spec(xSX, uSX, ySX, dSX, tSX, pxSX, pySX, n, m, p, nd, npx, npy, n
     DU = U - Uprev                                                  # (:163-166)
     quad_cost = cont_rhs = None
     if ContForm is True:                                            # (:102-111,153-158)
+        # The reference integrates  xdot = fx(x,u,d,t,px) + px  together with the quadrature of the stage cost over
+        # [0, h] with SUNDIALS IDAS (variable-step BDF, rel. tol 1e-6).  DEVIATION: a fixed-step classic RK4 with the
+        # model's Mx sub-steps is used instead (device and oracle alike) - IDAS is neither vendored nor smooth to 1e-8.
+        from .sx import simpleRK, vertcat as _vc
         cont_rhs = fx(X, U, d, t, pxk) + pxk
         ystat = Fy_model(xs, us, d, t, pyk)
         quad_cost = F_obj(X, U, Fy_model(X, U, d, t, pyk), xs, us, ystat)
-        Xnext = SX.zeros(n, 1)      # produced by the integrator, not by Fx_model
-        stage_cost = SX(0.0)
+        substeps = int(Fx_model.meta.get("substeps", 10))
+        qsym = SX.sym("q", 1)
+        frozen = _vc(U, par, pxk, pyk)
+        f_aug = Function("ocq_rhs", [_vc(X, qsym), frozen], [_vc(SX(cont_rhs), SX(quad_cost))])
+        end = simpleRK(f_aug, substeps)(_vc(X, SX(0.0)), frozen, h)
+        Xnext = end[0:n, :]
+        stage_cost = end[n, :]
     else:
         Xnext = Fx_model(X, U, h, d, t, pxk)                        # (:161)
         dx, du, dy = X, U, Y                                        # (:173-185)
@@ -142,7 +152,8 @@ def build_ocp_spec(xSX, uSX, ySX, dSX, tSX, pxSX, pySX, n, m, p, nd, npx, npy, n
                    w_lb=w_lb, w_ub=w_ub, g_lb=g_lb, g_ub=g_ub,
                    bounds=dict(xmin=xmin_v, xmax=xmax_v, umin=umin_v, umax=umax_v, ymin=ymin_v, ymax=ymax_v,
                                Dumin=Dumin_v, Dumax=Dumax_v),
-                   sol_opts=dict(sol_opts or {}), quad_cost=quad_cost, cont_rhs=cont_rhs)
+                   sol_opts=dict(sol_opts or {}), quad_cost=quad_cost, cont_rhs=cont_rhs,
+                   cont_substeps=(int(Fx_model.meta.get("substeps", 10)) if ContForm is True else 0))
 
 
 def opt_dyn(*args, **kwargs):

@@ -44,6 +44,22 @@ struct InstState {
     double filt[2 * MPCB_MAXFILT];
 };
 
+#if MPCB_CONTFORM
+// ContForm (Control_Calc.py:102-111,153-158): the OCP integrates xdot = fx + px together with the quadrature of the
+// stage cost; state [x; q], all other inputs frozen over the interval (time too - it is a parameter of the reference's
+// integrator call).  DEVIATION: classic RK4 with MPCB_CMX sub-steps instead of SUNDIALS IDAS.
+struct ContCtx { const double* u; const double* par; const double* pxk; const double* pyk; };
+struct SysCont {
+    static constexpr int NS = NX + 1, NM = MPCB_CMX;
+    typedef ContCtx Ctx;
+    MPCB_HDM void f(const double* x, const Ctx& c, double, double* o) { ocq_f(x, c.u, c.par, c.pxk, c.pyk, o); }
+    MPCB_HDM void f_vjp(const double* x, const Ctx& c, double, const double* nu, double* o) { ocq_f_vjp(x, c.u, c.par, c.pxk, c.pyk, nu, o); }
+    MPCB_HDM void f_sh(const double* x, const Ctx& c, double, const double* S, const double* nu, double* o, double* K, double* Hc) {
+        ocq_f_sh(x, c.u, c.par, c.pxk, c.pyk, S, nu, o, K, Hc);
+    }
+};
+#endif
+
 // Per-instance view of the solver workspace (all device pointers).
 struct OcpInst {
     double* w; double* wext; const double* par;      // w: internal iterate (NWI); wext: caller buffer (NW, reference layout)
@@ -249,7 +265,31 @@ MPCB_HD void ocp_eval_stage(OcpInst& I, const OcpShared& S, int k) {
     stage_params(I.par, k, d, px, py, &t0);
     double xn[NXA], A[NXA * NXA], Bm[NXA * NU], Hp[NZAP], l, g[NZA];
     ocp_cost_d(z, u, I.par, px, py, &l, g, Hp);          // Hp <- cost Hessian, then accumulate the rest
-#if NAUG == 0
+#if MPCB_CONTFORM
+    {   // dynamics and stage cost from one sweep over [x; q] with the adjoint seed [lam; 1]
+        constexpr int NS = NX + 1, NZS = NS + NU;
+        ContCtx cc; cc.u = u; cc.par = I.par; cc.pxk = px; cc.pyk = py;
+        double xt[NS], lt[NS], xe[NS], S[NS * NZS], Ht[NZS * (NZS + 1) / 2];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) { xt[i] = z[i]; lt[i] = lam[i]; }
+        xt[NX] = 0.0; lt[NX] = 1.0;
+#pragma unroll
+        for (int i = 0; i < NZS * (NZS + 1) / 2; ++i) Ht[i] = 0.0;
+        rk4_full_t<SysCont>(xt, cc, t0, lt, xe, S, Ht);
+        l = xe[NX];
+#pragma unroll
+        for (int j = 0; j < NZ; ++j) {
+            const int js = (j < NX) ? j : j + 1;          // skip the q0 column
+            g[j] = S[NX + NS * js];
+#pragma unroll
+            for (int i = 0; i < NX; ++i) { if (j < NX) A[i + NX * j] = S[i + NS * js]; else Bm[i + NX * (j - NX)] = S[i + NS * js]; }
+#pragma unroll
+            for (int i = 0; i <= j; ++i) { const int is = (i < NX) ? i : i + 1; Hp[tri(j, i)] += Ht[tri(js, is)]; }
+        }
+#pragma unroll
+        for (int i = 0; i < NX; ++i) xn[i] = xe[i];
+    }
+#elif NAUG == 0
     dyn_full(z, u, d, px, t0, lam, xn, A, Bm, Hp);
 #else
     {   // model part by the RK4 sweeps, then embedded into the augmented stage:  z+ = [Fx(x,u); u]
@@ -795,13 +835,27 @@ MPCB_HD void ocp_trial_stage(OcpInst& I, const OcpShared& S, int k) {
 #pragma unroll
     for (int i = 0; i < NU; ++i) u[i] = w[k * NZA + NXA + i] + al * dw[k * NZA + NXA + i];
     stage_params(I.par, k, d, px, py, &t0);
+    double th = 0.0, prod = 1.0, l;     // prod: product of slacks-to-bounds (one log per stage)
+#if MPCB_CONTFORM
+    {
+        ContCtx cc; cc.u = u; cc.par = I.par; cc.pxk = px; cc.pyk = py;
+        double xt[NX + 1], xe[NX + 1];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) xt[i] = z[i];
+        xt[NX] = 0.0;
+        rk4_value_t<SysCont>(xt, cc, t0, xe);
+#pragma unroll
+        for (int i = 0; i < NX; ++i) xn[i] = xe[i];
+        l = xe[NX];
+    }
+#else
     dyn_value(z, u, d, px, t0, xn);
 #pragma unroll
     for (int i = NX; i < NXA; ++i) xn[i] = u[i - NX];
-    double th = 0.0, prod = 1.0, l;     // prod: product of slacks-to-bounds (one log per stage)
+    ocp_cost(z, u, I.par, px, py, &l);
+#endif
 #pragma unroll
     for (int i = 0; i < NXA; ++i) th += fabs(xn[i] - (w[(k + 1) * NZA + i] + al * dw[(k + 1) * NZA + i]));
-    ocp_cost(z, u, I.par, px, py, &l);
 #if NG > 0
     {
         double Y[NG];

@@ -138,8 +138,8 @@ def generate_header(prob, ss_spec, ocp_spec, opts: Optional[Dict] = None) -> Dic
     # ---- OCP stage maps (Control_Calc.py:124-210) ---------------------------
     if ocp_spec is not None:
         o = ocp_spec
-        if o.flags["ContForm"] is True:
-            raise NotImplementedError("ContForm (integrated stage cost) is not on the device path yet")
+        if o.flags["ContForm"] is True and o.uses_uprev:
+            raise NotImplementedError("ContForm together with Delta-u terms is not on the device path")
         if o.term_eq is not None:
             raise NotImplementedError("TermCons (terminal equality) is not on the device path yet")
         # Delta-u costs / bounds couple u_k with u_{k-1} (Control_Calc.py:163-169,180-183): the device carries
@@ -154,9 +154,32 @@ def generate_header(prob, ss_spec, ocp_spec, opts: Optional[Dict] = None) -> Dic
         Z = vertcat(X, Up) if naug else X               # stage state seen by the kernels
         zz = vertcat(Z, U)
         ins_c = [("Z", Z), ("U", U), ("par", par), ("pxk", pxk), ("pyk", pyk)]
-        Hc, gc = hessian(o.stage_cost, zz)
-        fns.append(CFunction("ocp_cost", ins_c, [("l", o.stage_cost)]))
-        fns.append(CFunction("ocp_cost_d", ins_c, [("l", o.stage_cost), ("g", gc), ("H", tril_pack(Hc))]))
+        if o.flags["ContForm"] is True:
+            # stage cost = quadrature state of the integrator (Control_Calc.py:102-111,153-158): the right-hand side
+            # [fx + px; F_obj] on the state [x; q] with the products the RK4 sweeps need; ocp_cost* are then zero.
+            D.update(MPCB_CONTFORM=1, MPCB_CMX=int(o.cont_substeps))
+            q = SX.sym("q", 1)
+            xt = vertcat(X, q)
+            rhs_t = vertcat(SX(o.cont_rhs), SX(o.quad_cost))
+            ns = o.n + 1
+            base_q = [("xt", xt), ("U", U), ("par", par), ("pxk", pxk), ("pyk", pyk)]
+            nu_adj = SX.sym("nu", ns)
+            nuf = mtimes(nu_adj.T, rhs_t)
+            St = SX.sym("S", ns, ns + o.m)
+            Kt = mtimes(jacobian(rhs_t, xt), St) + horzcat(SX.zeros(ns, ns), jacobian(rhs_t, U))
+            Hft, _ = hessian(nuf, vertcat(xt, U))
+            dZt = vertcat(St, horzcat(SX.zeros(o.m, ns), SX.eye(o.m)))
+            fns.append(CFunction("ocq_f", base_q, [("xdot", rhs_t)]))
+            fns.append(CFunction("ocq_f_vjp", base_q + [("nu", nu_adj)], [("fxTnu", gradient(nuf, xt))]))
+            fns.append(CFunction("ocq_f_sh", base_q + [("S", St), ("nu", nu_adj)],
+                                 [("xdot", rhs_t), ("K", Kt), ("Hc", tril_pack(mtimes(dZt.T, mtimes(Hft, dZt))))]))
+            stage_cost = SX(0.0)
+        else:
+            D.update(MPCB_CONTFORM=0, MPCB_CMX=1)
+            stage_cost = o.stage_cost
+        Hc, gc = hessian(stage_cost, zz)
+        fns.append(CFunction("ocp_cost", ins_c, [("l", stage_cost)]))
+        fns.append(CFunction("ocp_cost_d", ins_c, [("l", stage_cost), ("g", gc), ("H", tril_pack(Hc))]))
         Ht, gt = hessian(o.term_cost, o.XN)
         fns.append(CFunction("ocp_term", [("XN", o.XN), ("par", par)], [("V", o.term_cost)]))
         fns.append(CFunction("ocp_term_d", [("XN", o.XN), ("par", par)],

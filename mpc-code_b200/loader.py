@@ -79,15 +79,21 @@ def shim_modules():
                 sys.modules[name] = mod
 
 
-def load_example(path: str, overrides: dict | None = None) -> dict:
+def load_example(path: str, overrides: dict | None = None, source_edits=()) -> dict:
     """Execute ``path`` on top of the default flags and return the resulting namespace.
 
     ``overrides`` are applied after execution (e.g. ``{"Nsim": 20}``); they cannot change
-    branches taken inside the file.
+    branches taken inside the file.  ``source_edits`` is a sequence of ``(old, new)`` text
+    replacements applied to the source before execution, for switches a file hard-codes
+    (e.g. ``("mhe_mod = 'on'", "mhe_mod = 'off'")`` in the reference's Ex_ENMPC.py:109).
     """
     path = os.path.abspath(path)
     with open(path, "r") as fh:
         source = fh.read()
+    for old, new in source_edits:
+        if old not in source:
+            raise ValueError("source edit %r does not match anything in %s" % (old, path))
+        source = source.replace(old, new)
     ns = default_namespace()
     ns["__name__"] = os.path.splitext(os.path.basename(path))[0]
     ns["__file__"] = path

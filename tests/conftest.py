@@ -150,3 +150,8 @@ def lmpc_cstr():
 @pytest.fixture(scope="session")
 def lmpc_wb():
     return _bundle("lmpc_wb")
+
+
+@pytest.fixture(scope="session")
+def enmpc():
+    return _bundle("enmpc_reactor")

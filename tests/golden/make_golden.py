@@ -107,8 +107,10 @@ def main():
     np.savez_compressed(os.path.join(HERE, "nmpc_oracle.npz"), **out)
     # ---- the two linear configurations: closed loop of the unmodified reference files (single instance, as shipped)
     lin = {}
-    for fname, tag, Ns in (("Ex_LMPC_CSTR.py", "cstr", 24), ("Ex_LMPC_WB.py", "wb", 20)):
-        prob_l = build_problem(load_example(os.path.join(REF, fname)))
+    for fname, tag, Ns in (("Ex_LMPC_CSTR.py", "cstr", 24), ("Ex_LMPC_WB.py", "wb", 20), ("Ex_ENMPC.py", "enmpc", 14)):
+        # Ex_ENMPC.py:109 hard-codes its estimator switch; its own EKF branch is selected (MHE is out of scope)
+        edits = [("mhe_mod = 'on'", "mhe_mod = 'off'")] if tag == "enmpc" else []
+        prob_l = build_problem(load_example(os.path.join(REF, fname), source_edits=edits))
         ss_l, ocp_l = make_specs(prob_l)
         mod_l = cmodel.build("ref_" + tag, prob_l, ocp_l, ss_l)
         rec = OracleLoop(prob_l, ss_l, ocp_l, mod_l).run(Nsim=Ns)

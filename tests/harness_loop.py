@@ -65,7 +65,7 @@ class HarnessLoop:
                          1 if has_db else 0)
             xhat, dhat = np.ascontiguousarray(xi[:, :nx]), np.ascontiguousarray(xi[:, nx:])
             rec["D_HAT"].append(dhat.copy())
-            ysp, usp, xsp = [rows(v) for v in p.defSP(t_k)]
+            ysp, usp, xsp = [rows(v) for v in (p.defSP(t_k) if p.defSP is not None else (np.zeros(ny), np.zeros(nu), np.zeros(nx)))]
             us_prev, xs_prev = us_k.copy(), xs_k.copy()
             par_ss = np.hstack([usp, ysp, xsp, dhat, us_prev, np.zeros((B, ny * nu)), tt[:, None], zx, zy])
             y0 = np.stack([b.oracle.orc_fy(x0_m[i], p.u0, dhat[i], t_k, p_yk[:, 0]).ravel() for i in range(B)])

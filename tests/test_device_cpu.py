@@ -159,3 +159,11 @@ def test_lmpc_wb_closed_loop_with_delta_u_cost(lmpc_wb):
     """BASELINE configs[2]: Delta-u penalty (DUForm) - the device carries u_{k-1} as extra stage state."""
     assert lmpc_wb.ocp.uses_uprev and lmpc_wb.prob.flags["DUForm"] is True
     _check_linear_loop(lmpc_wb, "wb")
+
+
+def test_enmpc_closed_loop_with_integrated_economic_cost(enmpc):
+    """BASELINE configs[3] (EKF branch): ContForm - the stage cost is a quadrature state of the RK4 sweep; the economic
+    cost is indefinite, so the delta_w inertia ladder of the Riccati sweep is exercised (first solve: 30 iterations)."""
+    assert enmpc.prob.flags["ContForm"] is True and enmpc.ocp.cont_substeps == 10
+    assert L["enmpc_ITER_DYN"][0] >= 20
+    _check_linear_loop(enmpc, "enmpc")

@@ -161,12 +161,12 @@ def test_full_size_batch_properties(nmpc, cp):
 L = np.load(os.path.join(GOLDEN, "lmpc_oracle.npz"))
 
 
-@pytest.mark.parametrize("name,tag", [("lmpc_cstr", "cstr"), ("lmpc_wb", "wb")])
+@pytest.mark.parametrize("name,tag", [("lmpc_cstr", "cstr"), ("lmpc_wb", "wb"), ("enmpc_reactor", "enmpc")])
 def test_linear_configs_closed_loop_match_oracle(name, tag, request):
     """Ex_LMPC_CSTR (Kalman filter, infeasible first steps) and Ex_LMPC_WB (Luenberger observer, Delta-u cost):
     a batch of identical instances must reproduce the single-instance oracle trajectory."""
     from mpc_code_b200.mpc_loop import CompiledProblem
-    bundle = request.getfixturevalue(name)
+    bundle = request.getfixturevalue({"enmpc_reactor": "enmpc"}.get(name, name))
     B, Ns = 5, L[tag + "_U"].shape[0]
     ctl = CompiledProblem(bundle.prob, name).controller(B)
     rec = ctl.run(Ns)
@@ -199,7 +199,8 @@ def test_wood_berry_full_batch(lmpc_wb):
     assert np.array_equal(u[:, 100:164, :], u2)
 
 
-@pytest.mark.parametrize("name,fixture", [("nmpc_cstr", "nmpc"), ("lmpc_cstr", "lmpc_cstr"), ("lmpc_wb", "lmpc_wb")])
+@pytest.mark.parametrize("name,fixture", [("nmpc_cstr", "nmpc"), ("lmpc_cstr", "lmpc_cstr"), ("lmpc_wb", "lmpc_wb"),
+                                          ("enmpc_reactor", "enmpc")])
 def test_fused_step_equals_the_python_loop(name, fixture, request):
     """`mpcb_step` (device-resident loop state, glue kernels) against the statement-by-statement loop of mpc_loop.py."""
     from mpc_code_b200.mpc_loop import CompiledProblem
