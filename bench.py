@@ -314,10 +314,11 @@ def run_gpu(args):
 
 
 def cp_ws_bytes(cp):
+    """Per-instance bytes touched per step (solver workspace incl. stage records + caller buffers), see DESIGN.md 5."""
     d = cp.library.dims
     nz = d.nx + d.nu
-    per_stage = d.nx * d.nx * 2 + d.nx * d.nu * 2 + nz * (nz + 1) // 2 + 2 * nz + 6 * d.nx + d.ng * (nz + 8) + 8
-    return 8 * (d.N * per_stage + 4 * d.nw + d.npar)
+    rec = nz * d.nx + d.nx + nz * nz + 7 * nz + d.ng * (nz + 10) + 10
+    return 8 * (d.N * (rec + 20 + 4 * d.nx + 6 * d.ng) + 5 * d.nw + d.npar)
 
 
 def main():
