@@ -34,7 +34,7 @@ class CFunction:
     """One generated function: name, ordered pointer arguments, body text, op statistics."""
 
     def __init__(self, name: str, inputs: Sequence[Tuple[str, SX]], outputs: Sequence[Tuple[str, SX]],
-                 skip_zero_outputs: bool = False):
+                 skip_zero_outputs: bool = False, shared_reciprocals: bool = False):
         self.name = name
         self.inputs = [(n, v if isinstance(v, SX) else SX(v)) for n, v in inputs]
         self.outputs = [(n, v if isinstance(v, SX) else SX(v)) for n, v in outputs]
@@ -42,6 +42,10 @@ class CFunction:
             if not v.is_symbolic():
                 raise ValueError("%s: input %s is not purely symbolic" % (name, n))
         self.skip_zero_outputs = skip_zero_outputs
+        # a / b is emitted as a * (1 / b) with ONE reciprocal per distinct denominator (and a literal for constant
+        # denominators): FP64 division is a ~12-instruction sequence on the GPU, and model right-hand sides and their
+        # derivatives divide by the same few quantities many times.  Changes results by at most an ulp per operation.
+        self.shared_reciprocals = shared_reciprocals
         self._flat_out = [e for _, o in self.outputs for e in o.elements()]
         self.counts = S.op_counts(self._flat_out)
         self.flops = int(sum(self.counts.values()))
@@ -62,6 +66,7 @@ class CFunction:
         order = S.topo_order(self._flat_out)
         # count uses so that single-use cheap nodes could be inlined; keep it simple: one temp per node
         used_inputs = set()
+        recips: Dict[int, str] = {}
         tcount = 0
         for n in order:
             if n.op == "sym":
@@ -74,7 +79,17 @@ class CFunction:
                 continue
             a = [ref[c.uid] for c in n.args]
             op = n.op
-            if op in _INFIX:
+            if op == "div" and self.shared_reciprocals:
+                den = n.args[1]
+                if den.op == "const":
+                    rhs = "%s * %s" % (a[0], _lit(1.0 / den.val))
+                else:
+                    if den.uid not in recips:
+                        rname = "r%d" % len(recips)
+                        lines.append("  const double %s = 1.0 / %s;" % (rname, a[1]))
+                        recips[den.uid] = rname
+                    rhs = recips[den.uid] if n.args[0] is S.ONE else "%s * %s" % (a[0], recips[den.uid])
+            elif op in _INFIX:
                 rhs = "%s %s %s" % (a[0], _INFIX[op], a[1])
             elif op == "neg":
                 rhs = "-%s" % a[0]

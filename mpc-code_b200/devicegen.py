@@ -220,6 +220,8 @@ def generate_header(prob, ss_spec, ocp_spec, opts: Optional[Dict] = None) -> Dic
     else:
         D["MPCB_HAS_TARGET"] = 0
 
+    for f in fns:
+        f.shared_reciprocals = True          # device code only; the oracle's generated C keeps true divisions
     flops = {f.name: f.flops for f in fns}
     table = " ".join('{"%s", %dL},' % (n, v) for n, v in flops.items())
     text = emit_header("MPCB_MODEL_H", D, fns, preamble="#define MPCB_FLOPS_TABLE " + table)
