@@ -729,18 +729,21 @@ MPCB_HD void ocp_kkt(OcpInst& I, const OcpShared& S, double* sm) {
     RecStream rs;
     rec_prefetch(rs, I.rec);
 #if defined(__CUDA_ARCH__) && (MPCB_KKT_LANES == 32)
-    static_assert(FREC_SZ <= 64, "forward record staging assumes at most two doubles per lane");
+    constexpr int FPL = (FREC_SZ + 31) / 32;            // forward-record doubles per lane
     double* Fs = sm + KktScratch::F;
-    double fpre0 = (lane < FREC_SZ) ? I.frec[lane] : 0.0, fpre1 = (lane + 32 < FREC_SZ) ? I.frec[lane + 32] : 0.0;
+    double fpre[FPL];
+#pragma unroll
+    for (int q = 0; q < FPL; ++q) { const int e = lane + 32 * q; fpre[q] = (e < FREC_SZ) ? I.frec[e] : 0.0; }
 #endif
     for (int k = 0; k < NH; ++k) {
 #if defined(__CUDA_ARCH__) && (MPCB_KKT_LANES == 32)
         W_SYNC();
-        if (lane < FREC_SZ) Fs[lane] = fpre0;
-        if (lane + 32 < FREC_SZ) Fs[lane + 32] = fpre1;
+#pragma unroll
+        for (int q = 0; q < FPL; ++q) { const int e = lane + 32 * q; if (e < FREC_SZ) Fs[e] = fpre[q]; }
         if (k + 1 < NH) {
             const double* fn = I.frec + (k + 1) * FREC_SZ;
-            fpre0 = (lane < FREC_SZ) ? fn[lane] : 0.0; fpre1 = (lane + 32 < FREC_SZ) ? fn[lane + 32] : 0.0;
+#pragma unroll
+            for (int q = 0; q < FPL; ++q) { const int e = lane + 32 * q; fpre[q] = (e < FREC_SZ) ? fn[e] : 0.0; }
         }
         const double* F = Fs;
 #else

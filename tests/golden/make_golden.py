@@ -118,6 +118,31 @@ def main():
         for key in ("U", "X_HAT", "D_HAT", "XS", "US", "Xp", "Yp", "F_DYN", "ITER_DYN", "STATUS_DYN", "STATUS_SS"):
             lin["%s_%s" % (tag, key)] = rec[key]
     np.savez_compressed(os.path.join(HERE, "lmpc_oracle.npz"), **lin)
+    # ---- synthetic family (BASELINE configs[4]): one mid-size member whose oracle (symbolic Hessian of the unrolled
+    #      RK4 graph, 8 states) takes minutes to build - hence a fixture; smaller members are checked live by the tests
+    if "--synthetic" in sys.argv:
+        import __graft_entry__ as entry
+        syn = {}
+        for name in ("syn_8_3_50",):
+            p_s, ss_s, ocp_s = entry._problem(name)
+            mod_s = cmodel.build(name, p_s, ocp_s, ss_s)
+            on_s = OcpNlp(ocp_s, mod_s)
+            rng_s = np.random.default_rng(5)
+            nxs, nus, Ns_ = p_s.nx, p_s.nu, p_s.N
+            nz_s = nxs + nus
+            w0s = np.zeros(ocp_s.nw)
+            pars, Ws, Fs, STs, ITs = [], [], [], [], []
+            for _ in range(4):
+                xh = rng_s.uniform(-1, 1, nxs)
+                par_s = np.concatenate([xh, np.zeros(nxs), np.zeros(nus), np.zeros(0), np.zeros(nus), [0.0], np.zeros(p_s.ny * nus),
+                                        np.zeros((p_s.npx + p_s.npy) * Ns_)])
+                lb, ub = ocp_s.w_lb.copy(), ocp_s.w_ub.copy(); lb[:nxs] = ub[:nxs] = xh
+                r = on_s.solve(w0s, par_s, lb, ub, opts=IpmOptions(max_iter=100))
+                pars.append(par_s); Ws.append(r.x); Fs.append(r.f); STs.append(r.status); ITs.append(r.iters)
+                print(name, r.return_status, r.iters, r.f)
+            syn.update({name + "_par": np.array(pars), name + "_w": np.array(Ws), name + "_f": np.array(Fs),
+                        name + "_status": np.array(STs), name + "_iters": np.array(ITs)})
+        np.savez_compressed(os.path.join(HERE, "synthetic_oracle.npz"), **syn)
     print("wrote fixtures")
 
 
