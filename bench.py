@@ -123,30 +123,39 @@ def run_reference(args):
 # GPU arm
 # ---------------------------------------------------------------------------------------------
 def _clock_sampler(path):
-    q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
     try:
-        return subprocess.Popen(["nvidia-smi", "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+        return subprocess.Popen(["nvidia-smi", "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "50"],
                                 stdout=open(path, "w"), stderr=subprocess.DEVNULL)
     except Exception:
         return None
 
 
-def _parse_clocks(path, gpu_index):
-    sm, smax, reasons = [], 0.0, set()
+def _parse_clocks(path, gpu_index, windows):
+    """Median SM clock and throttle reasons of the samples that fall inside the timed windows [(t0, t1), ...]."""
+    import datetime
+    sm, smax, reasons, n_all = [], 0.0, set(), 0
     try:
         for line in open(path):
             f = [x.strip() for x in line.split(",")]
-            if len(f) < 9 or not f[0].isdigit() or int(f[0]) != gpu_index:
+            if len(f) < 10 or not f[1].isdigit() or int(f[1]) != gpu_index:
                 continue
-            sm.append(float(f[1])); smax = max(smax, float(f[2]))
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+            n_all += 1
+            try:
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+            except ValueError:
+                continue
+            if not any(a - 0.05 <= ts <= b + 0.05 for a, b in windows):
+                continue
+            sm.append(float(f[2])); smax = max(smax, float(f[3]))
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[6:10]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
     except Exception:
         pass
     return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax or None, "reasons": sorted(reasons),
-            "samples": len(sm)}
+            "samples": len(sm), "samples_total": n_all}
 
 
 def stage_flops(cp):
@@ -193,29 +202,30 @@ def run_gpu(args):
         torch.cuda.synchronize(dev)
 
     # ---------------- device-resident closed loop (value) ----------------
+    clock_file = os.path.join(tempfile.gettempdir(), "mpcb_clocks_%d.csv" % os.getpid())
+    sampler = _clock_sampler(clock_file) if rank == 0 else None
+    windows = []
     ctl.reset(x0_p=x0, x0_m=x0)
     ys, us, stat = [], [], []
     for k in range(W):
         o = ctl.step_fused(noise_dev[k]); ys.append(o["Yp"]); us.append(o["U"].clone())
-    clock_file = os.path.join(tempfile.gettempdir(), "mpcb_clocks_%d.csv" % os.getpid())
-    sampler = _clock_sampler(clock_file) if rank == 0 else None
     ctl.h.set_profiling(True)
     launches0 = ctl.h.launches
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
     barrier()
+    t_w0 = time.time()
     ev[0].record()
     for k in range(K):
         o = ctl.step_fused(noise_dev[W + k])
         ev[k + 1].record()
         ys.append(o["Yp"]); us.append(o["U"].clone()); stat.append((o["STATUS_DYN"].clone(), o["ITER_DYN"].clone(), o["STATUS_SS"].clone()))
     barrier()
+    windows.append((t_w0, time.time()))
     elapsed_ms = ev[0].elapsed_time(ev[K])
     prof = ctl.h.profile()
     ctl.h.set_profiling(False)
     launches = ctl.h.launches - launches0
     step_ms = np.array([ev[k].elapsed_time(ev[k + 1]) for k in range(K)])
-    if sampler is not None:
-        sampler.terminate(); sampler.wait()
     t_all = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
@@ -231,6 +241,7 @@ def run_gpu(args):
         y_dev.copy_(y_host[k], non_blocking=True); o = ctl.step_fused(y_meas=y_dev); u_host[k].copy_(o["U"], non_blocking=True)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_w0 = time.time()
     e0.record()
     for k in range(W, total):
         y_dev.copy_(y_host[k], non_blocking=True)                    # H2D of this step's measurement
@@ -239,6 +250,10 @@ def run_gpu(args):
         torch.cuda.current_stream(dev).synchronize()                 # the caller needs u_k before the next sample
     e1.record()
     barrier()
+    windows.append((t_w0, time.time()))
+    if sampler is not None:
+        time.sleep(0.1)
+        sampler.terminate(); sampler.wait()
     t_e2e = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
@@ -292,7 +307,7 @@ def run_gpu(args):
         cpu_baseline = {"value": v, "unit": "steps/s", "cores": cores, "kind": "port",
                         "sample": "%d instances x 10 closed-loop steps of the same workload, one process per core (%.1f s); "
                                   "dense-KKT oracle port, not IPOPT" % (cores, wall)}
-    clocks = _parse_clocks(clock_file, local)
+    clocks = _parse_clocks(clock_file, local, windows)
     out = {
         "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": elapsed_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
