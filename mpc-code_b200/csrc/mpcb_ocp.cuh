@@ -325,7 +325,14 @@ MPCB_HD void ocp_eval_stage(OcpInst& I, const OcpShared& S, int k) {
             }
     }
 #endif
+#ifndef MPCB_VEC_REC
+#define MPCB_VEC_REC 1
+#endif
+#if MPCB_VEC_REC
+    double r[REC_SZ];          // the record is assembled in registers and written out with 128-bit stores at the end
+#else
     double* r = I.rec + k * REC_SZ;
+#endif
     double th = 0.0, prim = 0.0, ysum = 0.0, zsum = 0.0, nb = 0.0, pmin = 1e300, pmax = -1e300;
     double prod = 1.0;     // product of all slacks-to-bounds of the stage: one log instead of one per bound
 #pragma unroll
@@ -403,6 +410,18 @@ MPCB_HD void ocp_eval_stage(OcpInst& I, const OcpShared& S, int k) {
     for (int i = 0; i < NZA * NZA; ++i) r[R_M + i] = M[i];
     r[R_PART + 0] = l; r[R_PART + 1] = th; r[R_PART + 2] = dual; r[R_PART + 3] = prim; r[R_PART + 4] = ysum;
     r[R_PART + 5] = zsum; r[R_PART + 6] = nb; r[R_PART + 7] = pmin; r[R_PART + 8] = pmax; r[R_PART + 9] = log(prod);
+#if MPCB_VEC_REC
+    {
+        double* rg_ = I.rec + k * REC_SZ;               // 16-byte aligned: REC_SZ and the workspace offsets are even
+#ifdef __CUDA_ARCH__
+#pragma unroll
+        for (int i = 0; i < (R_PART + NPART + 1) / 2; ++i)
+            reinterpret_cast<double2*>(rg_)[i] = make_double2(r[2 * i], (2 * i + 1 < R_PART + NPART) ? r[2 * i + 1] : 0.0);
+#else
+        for (int i = 0; i < R_PART + NPART; ++i) rg_[i] = r[i];
+#endif
+    }
+#endif
     if (k == NH - 1) {
         double V, gN[NX], HN[NXP_ + 1];
         double* t = I.trec;
@@ -575,7 +594,11 @@ MPCB_HD bool ocp_riccati(OcpInst& I, double mu, double dwreg, double* sm) {
             double djj = M[(NXA + j) + NZA * (NXA + j)];
             for (int l = 0; l < j; ++l) djj -= L[j + NU * l] * L[j + NU * l];
             if (!(djj > 0.0)) { pd = false; djj = 1.0; }
+#ifdef __CUDA_ARCH__
+            const double inv = rsqrt(djj);
+#else
             const double inv = 1.0 / sqrt(djj);
+#endif
             Li[j] = inv;
             L[j + NU * j] = djj * inv;
             for (int i = j + 1; i < NU; ++i) {
@@ -720,36 +743,41 @@ MPCB_HD void ocp_kkt(OcpInst& I, const OcpShared& S, double* sm) {
         if (dwreg > 1e40) break;
     }
     if (!ok) { ocp_finish(I, S, -3, fobj); return; }
-    // ---- forward sweep (sequential over the stages): dw, the new multipliers, slack steps, and - fused -
-    //      fraction to the boundary (primal and dual), barrier objective and its directional derivative
-    double* dx = sm + KktScratch::dx; double* du = sm + KktScratch::du; double* dxn = sm + KktScratch::dxn;
-    double rp = 0.0, rd = 0.0, gphid = 0.0;       // largest primal / dual boundary ratios, directional derivative
-    for (int i = lane; i < NXA; i += N_LANES) { dx[i] = 0.0; I.dw[i] = 0.0; }
+    // ---- forward sweep, sequential part: only  du_k = K_k dx_k + k_k  and  dx_{k+1} = A dx_k + B du_k + c  (two lane
+    //      phases per stage; the [A|B], c head of the record and the K, k head of the forward record are prefetched
+    //      one stage ahead, one double per lane)
+    double* dxa = sm + KktScratch::dx; double* du = sm + KktScratch::du; double* dxb = sm + KktScratch::dxn;
+    for (int i = lane; i < NXA; i += N_LANES) { dxa[i] = 0.0; I.dw[i] = 0.0; }
+#if defined(__CUDA_ARCH__) && (MPCB_KKT_LANES == 32)
+    constexpr int NHEAD = R_C + NXA, NFH = FREC_P;              // doubles needed per stage: record head, forward-record head
+    constexpr int HPL = (NHEAD + NFH + 31) / 32;
+    double* Rs = sm + KktScratch::R;                            // staged: [record head | forward-record head]
+    double hpre[HPL];
+#pragma unroll
+    for (int q = 0; q < HPL; ++q) {
+        const int e = lane + 32 * q;
+        hpre[q] = (e < NHEAD) ? I.rec[e] : ((e < NHEAD + NFH) ? I.frec[e - NHEAD] : 0.0);
+    }
+#endif
     W_SYNC();
-    RecStream rs;
-    rec_prefetch(rs, I.rec);
-#if defined(__CUDA_ARCH__) && (MPCB_KKT_LANES == 32)
-    constexpr int FPL = (FREC_SZ + 31) / 32;            // forward-record doubles per lane
-    double* Fs = sm + KktScratch::F;
-    double fpre[FPL];
-#pragma unroll
-    for (int q = 0; q < FPL; ++q) { const int e = lane + 32 * q; fpre[q] = (e < FREC_SZ) ? I.frec[e] : 0.0; }
-#endif
     for (int k = 0; k < NH; ++k) {
+        double* dx = (k & 1) ? dxb : dxa; double* dxn = (k & 1) ? dxa : dxb;
 #if defined(__CUDA_ARCH__) && (MPCB_KKT_LANES == 32)
-        W_SYNC();
 #pragma unroll
-        for (int q = 0; q < FPL; ++q) { const int e = lane + 32 * q; if (e < FREC_SZ) Fs[e] = fpre[q]; }
+        for (int q = 0; q < HPL; ++q) { const int e = lane + 32 * q; if (e < NHEAD + NFH) Rs[e] = hpre[q]; }
         if (k + 1 < NH) {
-            const double* fn = I.frec + (k + 1) * FREC_SZ;
+            const double* rn = I.rec + (k + 1) * REC_SZ; const double* fn = I.frec + (k + 1) * FREC_SZ;
 #pragma unroll
-            for (int q = 0; q < FPL; ++q) { const int e = lane + 32 * q; fpre[q] = (e < FREC_SZ) ? fn[e] : 0.0; }
+            for (int q = 0; q < HPL; ++q) {
+                const int e = lane + 32 * q;
+                hpre[q] = (e < NHEAD) ? rn[e] : ((e < NHEAD + NFH) ? fn[e - NHEAD] : 0.0);
+            }
         }
-        const double* F = Fs;
+        W_SYNC();
+        const double* R = Rs; const double* F = Rs + NHEAD;
 #else
-        const double* F = I.frec + k * FREC_SZ;
+        const double* R = I.rec + k * REC_SZ; const double* F = I.frec + k * FREC_SZ;
 #endif
-        const double* R = stage_record(rs, I.rec + k * REC_SZ, (k + 1 < NH) ? I.rec + (k + 1) * REC_SZ : nullptr, sm);
         for (int i = lane; i < NU; i += N_LANES) {
             double a = F[FREC_KF + i];
             for (int j = 0; j < NXA; ++j) a += F[FREC_K + i + NU * j] * dx[j];
@@ -764,38 +792,42 @@ MPCB_HD void ocp_kkt(OcpInst& I, const OcpShared& S, double* sm) {
             dxn[i] = a;
             I.dw[(k + 1) * NZA + i] = a;
         }
-        // stage variables (x_k, u_k) against their bounds
-        for (int j = lane; j < NZA; j += N_LANES) {
-            const double dv = (j < NXA) ? dx[j] : du[j - NXA];
-            gphid += R[R_GL + j] * dv;
-            step_terms(dv, R[R_IL + j], R[R_IU + j], R[R_QL + j], R[R_QU + j], mu, &rp, &rd, &gphid);
+        W_SYNC();
+    }
+    // ---- stage-parallel part (lanes over stages): new dynamics multipliers, slack / multiplier steps of the range
+    //      rows, fraction to the boundary (primal and dual) and the directional derivative of the barrier function
+    double rp = 0.0, rd = 0.0, gphid = 0.0;       // largest primal / dual boundary ratios, directional derivative
+    for (int k = lane; k <= NH; k += N_LANES) {
+        if (k == NH) {
+            const double* t = I.trec;
+            for (int j = 0; j < NXA; ++j) {
+                const double dv = I.dw[NH * NZA + j];
+                gphid += t[T_GN + j] * dv;
+                step_terms(dv, t[T_IL + j], t[T_IU + j], t[T_QL + j], t[T_QU + j], mu, &rp, &rd, &gphid);
+            }
+            continue;
+        }
+        const double* R = I.rec + k * REC_SZ; const double* F = I.frec + k * FREC_SZ;
+        const double* dv = I.dw + k * NZA; const double* dxn = I.dw + (k + 1) * NZA;
+        for (int i = 0; i < NXA; ++i) {
+            double a = F[FREC_PV + i];
+            for (int j = 0; j < NXA; ++j) a += F[FREC_P + i + NXA * j] * dxn[j];
+            I.lamn[k * NXA + i] = a;
+        }
+        for (int j = 0; j < NZA; ++j) {
+            gphid += R[R_GL + j] * dv[j];
+            step_terms(dv[j], R[R_IL + j], R[R_IU + j], R[R_QL + j], R[R_QU + j], mu, &rp, &rd, &gphid);
         }
 #if NG > 0
-        for (int r = lane; r < NG; r += N_LANES) {
+        for (int r = 0; r < NG; ++r) {
             double dsr = R[R_RG + r];
-            for (int j = 0; j < NZA; ++j) dsr += R[R_G + r + NG * j] * ((j < NXA) ? dx[j] : du[j - NXA]);
+            for (int j = 0; j < NZA; ++j) dsr += R[R_G + r + NG * j] * dv[j];
             const double b = -mu * R[R_ISL + r] + mu * R[R_ISU + r];
             I.ds[k * NG + r] = dsr;
             I.dym[k * NG + r] = (R[R_SG + r] + dwreg) * dsr + b - R[R_YM + r];
             step_terms(dsr, R[R_ISL + r], R[R_ISU + r], R[R_QSL + r], R[R_QSU + r], mu, &rp, &rd, &gphid);
         }
 #endif
-        W_SYNC();
-        for (int i = lane; i < NXA; i += N_LANES) {
-            double a = F[FREC_PV + i];
-            for (int j = 0; j < NXA; ++j) a += F[FREC_P + i + NXA * j] * dxn[j];
-            I.lamn[k * NXA + i] = a;
-        }
-        W_SYNC();
-        for (int i = lane; i < NXA; i += N_LANES) dx[i] = dxn[i];
-        W_SYNC();
-    }
-    {
-        const double* t = I.trec;
-        for (int j = lane; j < NXA; j += N_LANES) {
-            gphid += t[T_GN + j] * dx[j];
-            step_terms(dx[j], t[T_IL + j], t[T_IU + j], t[T_QL + j], t[T_QU + j], mu, &rp, &rd, &gphid);
-        }
     }
     rp = W_MAX(rp); rd = W_MAX(rd); gphid = W_SUM(gphid);
     const double amax = (rp > tau) ? tau / rp : 1.0;

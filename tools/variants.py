@@ -11,11 +11,11 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 VARIANTS = {
-    "lanes1": "",
-    "lanes32_w4": "-DMPCB_KKT_LANES=32",
-    "lanes32_w2": "-DMPCB_KKT_LANES=32 -DKKT_WARPS=2",
-    "lanes32_w8": "-DMPCB_KKT_LANES=32 -DKKT_WARPS=8",
-    "lanes32_w4_eval128x3": "-DMPCB_KKT_LANES=32 -DMPCB_EVAL_MINBLOCKS=3",
+    "default": "",
+    "scalar_record_stores": "-DMPCB_VEC_REC=0",
+    "eval128x2": "-DMPCB_EVAL_MINBLOCKS=2",
+    "kkt_warps2": "-DKKT_WARPS=2",
+    "kkt_warps8": "-DKKT_WARPS=8",
 }
 
 if __name__ == "__main__":
