@@ -357,29 +357,38 @@ MPCB_HD void est_update(int est_type, const double* y_meas, const double* u, dou
                 for (int l = 0; l < NXI; ++l) a += C[i + NY * l] * PCt[l * NY + j];
                 Sm[i * NY + j] = a;
             }
-        // K = P C' S^{-1} by Cholesky of S (symmetric positive definite)
-        for (int j = 0; j < NY; ++j) {
-            double djj = Sm[j * NY + j];
-            for (int l = 0; l < j; ++l) djj -= L[j * NY + l] * L[j * NY + l];
-            djj = sqrt(djj);
-            L[j * NY + j] = djj;
-            for (int i = j + 1; i < NY; ++i) {
-                double a = 0.5 * (Sm[i * NY + j] + Sm[j * NY + i]);
-                for (int l = 0; l < j; ++l) a -= L[i * NY + l] * L[j * NY + l];
-                L[i * NY + j] = a / djj;
+        // K = P C' S^{-1}: general LU with partial pivoting on S' (K S = P C'  <=>  S' K' = (P C')'), as the
+        // reference's `solve(S.T, (P C').T).T` (Estimator.py:297,352).  S is NOT symmetrised: the term C E C' of an
+        // antisymmetric round-off E in P is what makes the error map E -> A(I-KC) E (I-KC)'A' contract; dropping it
+        // lets E grow like |eig(A)|^2 per step for an open-loop unstable model.
+        int piv[NY];
+        for (int i = 0; i < NY; ++i)
+            for (int j = 0; j < NY; ++j) L[i * NY + j] = Sm[j * NY + i];         // L := S'
+        for (int c = 0; c < NY; ++c) {
+            int pr = c; double best = fabs(L[c * NY + c]);
+            for (int i = c + 1; i < NY; ++i) if (fabs(L[i * NY + c]) > best) { best = fabs(L[i * NY + c]); pr = i; }
+            piv[c] = pr;
+            if (pr != c) for (int j = 0; j < NY; ++j) { double tmp = L[c * NY + j]; L[c * NY + j] = L[pr * NY + j]; L[pr * NY + j] = tmp; }
+            double inv = 1.0 / L[c * NY + c];
+            for (int i = c + 1; i < NY; ++i) {
+                double f = L[i * NY + c] * inv;
+                L[i * NY + c] = f;
+                for (int j = c + 1; j < NY; ++j) L[i * NY + j] -= f * L[c * NY + j];
             }
         }
         double Kg[NXI * NY];
         for (int r = 0; r < NXI; ++r) {
             double yv[NY];
-            for (int i = 0; i < NY; ++i) {
-                double a = PCt[r * NY + i];
+            for (int i = 0; i < NY; ++i) yv[i] = PCt[r * NY + i];
+            for (int c = 0; c < NY; ++c) if (piv[c] != c) { double tmp = yv[c]; yv[c] = yv[piv[c]]; yv[piv[c]] = tmp; }
+            for (int i = 1; i < NY; ++i) {
+                double a = yv[i];
                 for (int l = 0; l < i; ++l) a -= L[i * NY + l] * yv[l];
-                yv[i] = a / L[i * NY + i];
+                yv[i] = a;
             }
             for (int i = NY - 1; i >= 0; --i) {
                 double a = yv[i];
-                for (int l = i + 1; l < NY; ++l) a -= L[l * NY + i] * yv[l];
+                for (int l = i + 1; l < NY; ++l) a -= L[i * NY + l] * yv[l];
                 yv[i] = a / L[i * NY + i];
             }
             for (int i = 0; i < NY; ++i) Kg[r * NY + i] = yv[i];

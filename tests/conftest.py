@@ -155,3 +155,8 @@ def lmpc_wb():
 @pytest.fixture(scope="session")
 def enmpc():
     return _bundle("enmpc_reactor")
+
+
+@pytest.fixture(scope="session")
+def lmpc_nlplant():
+    return _bundle("lmpc_nlplant")
