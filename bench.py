@@ -203,7 +203,7 @@ def run_gpu(args):
 
     # ---------------- device-resident closed loop (value) ----------------
     clock_file = os.path.join(tempfile.gettempdir(), "mpcb_clocks_%d.csv" % os.getpid())
-    sampler = _clock_sampler(clock_file) if rank == 0 else None
+    sampler = _clock_sampler(clock_file) if rank == 0 and not os.environ.get("MPCB_BENCH_NOSAMPLER") else None
     windows = []
     ctl.reset(x0_p=x0, x0_m=x0)
     ys, us, stat = [], [], []
@@ -317,6 +317,7 @@ def run_gpu(args):
                    "batch_per_gpu": B, "global_batch": world * B, "parallelism": "instances sharded, %d rank(s)" % world,
                    "cache": "per-step working set %.0f MB per GPU > 126 MB L2 (no flush needed)" % (B * cp_ws_bytes(cp) / 1e6)},
         "p50_step_latency_ms": float(np.median(step_ms)), "p99_step_latency_ms": float(np.percentile(step_ms, 99)),
+        "slowest_steps": [[int(i), float(step_ms[i])] for i in np.argsort(-step_ms)[:3]],
         "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": B * prob.ny * 8, "d2h_bytes_per_step": B * prob.nu * 8,
                 "replay_max_abs_du": replay_err},
         "gpu_launches": int(launches),

@@ -239,7 +239,7 @@ class BatchedMpc:
         self.h.loop_reset(self.xhat_k, self.u_k, self.dhat_k if self.prob.nd else None, self.P_k)
         self._fused = True
 
-    def step_fused(self, noise=None, y_meas=None) -> Dict[str, object]:
+    def step_fused(self, noise=None, y_meas=None, record_prediction: bool = False) -> Dict[str, object]:
         """One closed-loop step with estimator, target, OCP and extraction done by `mpcb_step`.  Same semantics and
         results as `step` (tests compare them); only the plant simulation and the set-point lookup stay on the host."""
         if not getattr(self, "_fused", False):
@@ -257,6 +257,8 @@ class BatchedMpc:
         px = row(p_xk.reshape(-1, order="F")) if varying else None
         py = row(p_yk.reshape(-1, order="F")) if varying else None
         out: Dict[str, object] = {}
+        if record_prediction:                               # x(k|k-1) as the reference logs it (MPC_code.py:520)
+            out["X_HAT"] = h.loop_state()[0][:, :p.nx].contiguous()
         if y_meas is None:
             out["Xp"] = self.x_k.clone()
             if p.flags["Fp_nominal"] is True:
@@ -288,7 +290,7 @@ class BatchedMpc:
         for k in range(Nsim):
             if fused:
                 o = {key: (val.clone() if isinstance(val, t.Tensor) else val)
-                     for key, val in self.step_fused(None if noise is None else noise[k]).items()}
+                     for key, val in self.step_fused(None if noise is None else noise[k], record_prediction=True).items()}
             else:
                 o = self.step(None if noise is None else noise[k], None if state_noise is None else state_noise[k])
             for key, val in o.items():
