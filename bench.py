@@ -205,6 +205,11 @@ def run_gpu(args):
     clock_file = os.path.join(tempfile.gettempdir(), "mpcb_clocks_%d.csv" % os.getpid())
     sampler = _clock_sampler(clock_file) if rank == 0 and not os.environ.get("MPCB_BENCH_NOSAMPLER") else None
     windows = []
+    if sampler is not None:                 # let nvidia-smi finish its NVML start-up (it stalls launches) before timing
+        t_wait = time.time()
+        while time.time() - t_wait < 5.0 and (not os.path.exists(clock_file) or os.path.getsize(clock_file) == 0):
+            time.sleep(0.05)
+        time.sleep(0.2)
     ctl.reset(x0_p=x0, x0_m=x0)
     ys, us, stat = [], [], []
     for k in range(W):

@@ -15,7 +15,7 @@ from . import symbolic as S
 from .sx import SX
 
 _INFIX = {"add": "+", "sub": "-", "mul": "*", "div": "/"}
-_CALL1 = {"exp": "exp", "log": "log", "sqrt": "sqrt", "sin": "sin", "cos": "cos", "tan": "tan",
+_CALL1 = {"exp": "MPCB_EXP", "log": "log", "sqrt": "sqrt", "sin": "sin", "cos": "cos", "tan": "tan",
           "tanh": "tanh", "fabs": "fabs", "asin": "asin", "acos": "acos", "atan": "atan",
           "sinh": "sinh", "cosh": "cosh"}
 _CMP = {"lt": "<", "le": "<=", "eq": "==", "ne": "!="}
@@ -34,8 +34,13 @@ class CFunction:
     """One generated function: name, ordered pointer arguments, body text, op statistics."""
 
     def __init__(self, name: str, inputs: Sequence[Tuple[str, SX]], outputs: Sequence[Tuple[str, SX]],
-                 skip_zero_outputs: bool = False, shared_reciprocals: bool = False):
+                 skip_zero_outputs: bool = False, shared_reciprocals: bool = False, cache_in=None):
         self.name = name
+        # cache_in = (argument name, entries): values of expensive sub-expressions computed by ANOTHER generated function
+        # at the same point and handed in through an extra ``const double*`` argument instead of being recomputed
+        # (see `expensive_entries`).  entries[i] = ("node", expr) -> arg[i] replaces that node;
+        # ("recip", den) -> arg[i] is 1/den and replaces the shared reciprocal of that denominator.
+        self.cache_in = cache_in
         self.inputs = [(n, v if isinstance(v, SX) else SX(v)) for n, v in inputs]
         self.outputs = [(n, v if isinstance(v, SX) else SX(v)) for n, v in outputs]
         for n, v in self.inputs:
@@ -52,7 +57,10 @@ class CFunction:
 
     # -- text ------------------------------------------------------------------
     def signature(self, qualifier="MPCB_FN") -> str:
-        args = ["const double* %s" % n for n, _ in self.inputs] + ["double* %s" % n for n, _ in self.outputs]
+        args = ["const double* %s" % n for n, _ in self.inputs]
+        if self.cache_in is not None:
+            args.append("const double* %s" % self.cache_in[0])
+        args += ["double* %s" % n for n, _ in self.outputs]
         return "%s void %s(%s)" % (qualifier, self.name, ", ".join(args))
 
     def source(self, qualifier="MPCB_FN") -> str:
@@ -67,8 +75,21 @@ class CFunction:
         # count uses so that single-use cheap nodes could be inlined; keep it simple: one temp per node
         used_inputs = set()
         recips: Dict[int, str] = {}
+        cut_nodes: Dict[int, str] = {}
+        if self.cache_in is not None:
+            cname, entries = self.cache_in
+            for i, (kind, e) in enumerate(entries):
+                if kind == "node":
+                    cut_nodes[e.uid] = "%s[%d]" % (cname, i)
+                else:
+                    recips[e.uid] = "%s[%d]" % (cname, i)
+            live = live_nodes(self._flat_out, set(cut_nodes), set(recips) if self.shared_reciprocals else set())
+            order = [n for n in order if n.uid in live]
         tcount = 0
         for n in order:
+            if n.uid in cut_nodes:
+                ref[n.uid] = cut_nodes[n.uid]
+                continue
             if n.op == "sym":
                 if n.uid not in known:
                     raise ValueError("%s: free symbol %s" % (self.name, n.val))
@@ -77,7 +98,7 @@ class CFunction:
             if n.op == "const":
                 ref[n.uid] = _lit(n.val)
                 continue
-            a = [ref[c.uid] for c in n.args]
+            a = [ref.get(c.uid) for c in n.args]        # None only for a denominator hidden behind a cached reciprocal
             op = n.op
             if op == "div" and self.shared_reciprocals:
                 den = n.args[1]
@@ -140,6 +161,62 @@ class CFunction:
         return "\n".join([head] + voids + lines + ["}"]) + "\n"
 
 
+EXPENSIVE_OPS = frozenset(("exp", "log", "sqrt", "sin", "cos", "tan", "tanh", "asin", "acos", "atan", "sinh", "cosh",
+                           "pow", "atan2"))
+
+
+def live_nodes(roots, cut_nodes, cut_recips):
+    """uids reachable from ``roots`` when cached nodes are leaves and cached reciprocals hide their denominators."""
+    live, stack = set(), list(roots)
+    while stack:
+        n = stack.pop()
+        if n.uid in live:
+            continue
+        live.add(n.uid)
+        if n.uid in cut_nodes:
+            continue
+        if n.op == "div" and n.args[1].uid in cut_recips:
+            stack.append(n.args[0])
+            continue
+        stack.extend(n.args)
+    return live
+
+
+def expensive_entries(consumers, tainted, shared_reciprocals=True):
+    """Expensive sub-expressions (transcendentals, reciprocals of non-constant denominators) of the output lists in
+    ``consumers`` that do not depend on the symbols in ``tainted`` - i.e. that a producer evaluated at the same point
+    can compute once and pass on.  Entries that end up unused once the others are cut are dropped."""
+    roots = [e for c in consumers for e in c]
+    order = S.topo_order(roots)
+    taint = {e.uid for e in tainted}
+    dep: Dict[int, bool] = {}
+    for n in order:
+        dep[n.uid] = (n.uid in taint) if n.op == "sym" else any(dep[a.uid] for a in n.args)
+    entries, seen_den = [], set()
+    for n in order:
+        if n.op in EXPENSIVE_OPS and not dep[n.uid] and any(a.op != "const" for a in n.args):
+            entries.append(("node", n))
+        if shared_reciprocals and n.op == "div":
+            den = n.args[1]
+            if den.op != "const" and not dep[den.uid] and den.uid not in seen_den:
+                seen_den.add(den.uid)
+                entries.append(("recip", den))
+    while True:                                          # drop entries hidden behind other entries
+        cut_n = {e.uid for k, e in entries if k == "node"}
+        cut_r = {e.uid for k, e in entries if k == "recip"}
+        live = live_nodes(roots, cut_n, cut_r)
+        used_r = {n.args[1].uid for n in order if n.uid in live and n.op == "div" and n.uid not in cut_n}
+        keep = [(k, e) for k, e in entries if (k == "node" and e.uid in live) or (k == "recip" and e.uid in used_r)]
+        if len(keep) == len(entries):
+            return entries
+        entries = keep
+
+
+def cache_expressions(entries) -> SX:
+    """The values a producer must write for `entries` (in order)."""
+    return SX([e if k == "node" else S.div(S.ONE, e) for k, e in entries])
+
+
 def emit_header(guard: str, defines: Dict[str, object], functions: Sequence[CFunction], preamble: str = "") -> str:
     """A self-contained header: size/flag macros followed by the generated functions."""
     out = ["// GENERATED by mpc_code_b200.codegen - do not edit.",
@@ -154,6 +231,7 @@ def emit_header(guard: str, defines: Dict[str, object], functions: Sequence[CFun
            "#endif", ""]
     if preamble:
         out.append(preamble)
+    out += ["#ifndef MPCB_EXP", "#define MPCB_EXP exp", "#endif", ""]
     for k, v in defines.items():
         if isinstance(v, bool):
             v = int(v)

@@ -49,9 +49,22 @@ struct InstState {
 // stage cost; state [x; q], all other inputs frozen over the interval (time too - it is a parameter of the reference's
 // integrator call).  DEVIATION: classic RK4 with MPCB_CMX sub-steps instead of SUNDIALS IDAS.
 struct ContCtx { const double* u; const double* par; const double* pxk; const double* pyk; };
+#ifndef MPCB_OCQ_NC
+#define MPCB_OCQ_NC 0
+#endif
 struct SysCont {
-    static constexpr int NS = NX + 1, NM = MPCB_CMX;
+    static constexpr int NS = NX + 1, NM = MPCB_CMX, NC = MPCB_OCQ_NC;
     typedef ContCtx Ctx;
+#if MPCB_OCQ_NC > 0
+    MPCB_HDM void f_c(const double* x, const Ctx& c, double, double* o, double* cache) { ocq_f_c(x, c.u, c.par, c.pxk, c.pyk, o, cache); }
+    MPCB_HDM void f_vjp_c(const double* x, const Ctx& c, double, const double* nu, const double* cache, double* o) {
+        ocq_f_vjp_c(x, c.u, c.par, c.pxk, c.pyk, nu, cache, o);
+    }
+    MPCB_HDM void f_sh_c(const double* x, const Ctx& c, double, const double* S, const double* nu, const double* cache,
+                         double* o, double* K, double* Hc) {
+        ocq_f_sh_c(x, c.u, c.par, c.pxk, c.pyk, S, nu, cache, o, K, Hc);
+    }
+#endif
     MPCB_HDM void f(const double* x, const Ctx& c, double, double* o) { ocq_f(x, c.u, c.par, c.pxk, c.pyk, o); }
     MPCB_HDM void f_vjp(const double* x, const Ctx& c, double, const double* nu, double* o) { ocq_f_vjp(x, c.u, c.par, c.pxk, c.pyk, nu, o); }
     MPCB_HDM void f_sh(const double* x, const Ctx& c, double, const double* S, const double* nu, double* o, double* K, double* Hc) {

@@ -17,7 +17,7 @@ from typing import Dict, List, Optional
 import numpy as np
 
 from . import symbolic as S
-from .codegen import CFunction, emit_header
+from .codegen import CFunction, cache_expressions, emit_header, expensive_entries
 from .sx import SX, Function, gradient, hessian, jacobian, mtimes, vertcat, horzcat
 
 
@@ -29,6 +29,19 @@ def tril_pack(H: SX) -> SX:
 def _depends_on(expr: SX, var: SX) -> bool:
     ids = {e.uid for e in var.elements()}
     return any(s.uid in ids for s in S.symbols_of(expr.elements()))
+
+
+def _cached_variants(prefix: str, base, f, vjp_in, vjp_out, sh_in, sh_out, tainted) -> List[CFunction]:
+    """``<prefix>f_c`` (value + stage cache), ``f_vjp_c`` / ``f_sh_c`` (take the cache): the three RK4 sweeps visit
+    the same stage points, so transcendentals and reciprocals of the right-hand side are evaluated once per point
+    instead of three times.  Empty when the right-hand side has nothing expensive to share."""
+    consumers = [[e for _, o in vjp_out for e in SX(o).elements()], [e for _, o in sh_out for e in SX(o).elements()]]
+    entries = expensive_entries(consumers, tainted)
+    if not entries:
+        return []
+    return [CFunction(prefix + "f_c", base, [("xdot", f), ("cache", cache_expressions(entries))]),
+            CFunction(prefix + "f_vjp_c", base + vjp_in, vjp_out, cache_in=("cache", entries)),
+            CFunction(prefix + "f_sh_c", base + sh_in, sh_out, cache_in=("cache", entries))]
 
 
 def _rhs_functions(prefix: str, rhs: Function, nx: int, nu: int, nd: int, npx: int, nxi: int) -> List[CFunction]:
@@ -51,8 +64,10 @@ def _rhs_functions(prefix: str, rhs: Function, nx: int, nu: int, nd: int, npx: i
     Hf, _ = hessian(nuf, zz)
     dZ = vertcat(Sxu, horzcat(SX.zeros(nu, nx), SX.eye(nu)))
     Hc = mtimes(dZ.T, mtimes(Hf, dZ))
-    fns.append(CFunction(prefix + "f_sh", base + [("S", Sxu), ("nu", nu_adj)],
-                         [("xdot", f), ("K", K), ("Hc", tril_pack(Hc))]))
+    sh_out = [("xdot", f), ("K", K), ("Hc", tril_pack(Hc))]
+    fns.append(CFunction(prefix + "f_sh", base + [("S", Sxu), ("nu", nu_adj)], sh_out))
+    fns += _cached_variants(prefix, base, f, [("nu", nu_adj)], [("fxTnu", gradient(nuf, x))],
+                            [("S", Sxu), ("nu", nu_adj)], sh_out, list(nu_adj.elements()) + list(Sxu.elements()))
     # sensitivities with respect to xi = (x0[, d]) for the estimator
     Sxi = SX.sym("S", nx, nxi)
     Kd = mtimes(fx, Sxi)
@@ -96,6 +111,7 @@ def generate_header(prob, ss_spec, ocp_spec, opts: Optional[Dict] = None) -> Dic
         D["MPCB_DYN_RK4"] = 1
         D["MPCB_MX"] = int(prob.Fx_model.meta["substeps"])
         fns += _rhs_functions("mdl_", prob.Fx_model.meta["rhs"], nx, nu, nd, npx, prob.nxi)
+        D["MPCB_MDL_NC"] = next((f.outputs[1][1].numel() for f in fns if f.name == "mdl_f_c"), 0)
         d_, px_ = SX.sym("d", nd), SX.sym("px", npx)
         post = prob.Fx_model.meta["post"](d_, px_)
         fns.append(CFunction("mdl_post", [("d", d_), ("px", px_)], [("post", post), ("Jd", jacobian(post, d_))]))
@@ -169,10 +185,14 @@ def generate_header(prob, ss_spec, ocp_spec, opts: Optional[Dict] = None) -> Dic
             Kt = mtimes(jacobian(rhs_t, xt), St) + horzcat(SX.zeros(ns, ns), jacobian(rhs_t, U))
             Hft, _ = hessian(nuf, vertcat(xt, U))
             dZt = vertcat(St, horzcat(SX.zeros(o.m, ns), SX.eye(o.m)))
+            sh_out = [("xdot", rhs_t), ("K", Kt), ("Hc", tril_pack(mtimes(dZt.T, mtimes(Hft, dZt))))]
             fns.append(CFunction("ocq_f", base_q, [("xdot", rhs_t)]))
             fns.append(CFunction("ocq_f_vjp", base_q + [("nu", nu_adj)], [("fxTnu", gradient(nuf, xt))]))
-            fns.append(CFunction("ocq_f_sh", base_q + [("S", St), ("nu", nu_adj)],
-                                 [("xdot", rhs_t), ("K", Kt), ("Hc", tril_pack(mtimes(dZt.T, mtimes(Hft, dZt))))]))
+            fns.append(CFunction("ocq_f_sh", base_q + [("S", St), ("nu", nu_adj)], sh_out))
+            cached = _cached_variants("ocq_", base_q, rhs_t, [("nu", nu_adj)], [("fxTnu", gradient(nuf, xt))],
+                                      [("S", St), ("nu", nu_adj)], sh_out, list(nu_adj.elements()) + list(St.elements()))
+            fns += cached
+            D["MPCB_OCQ_NC"] = cached[0].outputs[1][1].numel() if cached else 0
             stage_cost = SX(0.0)
         else:
             D.update(MPCB_CONTFORM=0, MPCB_CMX=1)
