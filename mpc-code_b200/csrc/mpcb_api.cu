@@ -64,16 +64,17 @@ __global__ void __launch_bounds__(MPCB_EVAL_BLOCK, MPCB_EVAL_MINBLOCKS) k_ocp_ev
 #ifndef KKT_WARPS
 #define KKT_WARPS 4
 #endif
-#if MPCB_KKT_LANES == 32
+#if MPCB_KKT_LANES > 1
 __global__ void __launch_bounds__(32 * KKT_WARPS) k_ocp_kkt(OcpArgs a) {
-    __shared__ double scratch[KKT_WARPS][KktScratch::total];
-    const int inst = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    constexpr int GROUPS = 32 * KKT_WARPS / MPCB_KKT_LANES;        // instances per block
+    __shared__ double scratch[GROUPS][KktScratch::total];
+    const int inst = (blockIdx.x * blockDim.x + threadIdx.x) / MPCB_KKT_LANES;
     if (inst >= a.B) return;
     if (a.st[inst].state != ST_EVAL) return;
     OcpInst I = ocp_view(a, inst);
-    ocp_kkt(I, a.S, scratch[threadIdx.x >> 5]);
+    ocp_kkt(I, a.S, scratch[threadIdx.x / MPCB_KKT_LANES]);
 }
-#define KKT_GRID(B) nblk((long)(B) * 32, 32 * KKT_WARPS), 32 * KKT_WARPS
+#define KKT_GRID(B) nblk((long)(B) * MPCB_KKT_LANES, 32 * KKT_WARPS), 32 * KKT_WARPS
 #else
 __global__ void __launch_bounds__(32) k_ocp_kkt(OcpArgs a) {
     const int inst = blockIdx.x * blockDim.x + threadIdx.x;
@@ -245,68 +246,78 @@ __global__ void k_step_pre(int B, const double* t, const double* sp, LoopState L
 }
 
 // after the target solve: status gate (:714-718), par (Control_Calc.py:43-57 order, MPC_code.py:769-772), warm start (:740-764)
+// One WARP per instance: the bulk of the work is moving the NW-long iterate (shifted warm start) and the parameter
+// rows, which lanes do with coalesced strided copies; one thread per instance spent 0.2 ms per step on serial copies.
 __global__ void k_step_mid(int B, int first, const double* t, const double* px, const double* py, LoopState L,
                            double* xs_out, double* us_out) {
-    const int inst = blockIdx.x * blockDim.x + threadIdx.x;
+    const int inst = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (inst >= B) return;
     double* xs = L.xs + (size_t)inst * NX; double* us = L.us + (size_t)inst * NU;
     const double* wss = L.wss + (size_t)inst * NWS;
-    double xs_prev[NX], us_prev[NU];
-    for (int i = 0; i < NX; ++i) xs_prev[i] = xs[i];
-    for (int i = 0; i < NU; ++i) us_prev[i] = us[i];
-    if (L.ss_status[inst] != 2) {
-        for (int i = 0; i < NX; ++i) xs[i] = wss[i];
-        for (int i = 0; i < NU; ++i) us[i] = wss[NX + i];
-    }
-    for (int i = 0; i < NX; ++i) xs_out[(size_t)inst * NX + i] = xs[i];
-    for (int i = 0; i < NU; ++i) us_out[(size_t)inst * NU + i] = us[i];
+    const bool ss_ok = L.ss_status[inst] != 2;
+    double xs_prev[NX], us_prev[NU], xs_new[NX], us_new[NU];
+    for (int i = 0; i < NX; ++i) { xs_prev[i] = xs[i]; xs_new[i] = ss_ok ? wss[i] : xs_prev[i]; }
+    for (int i = 0; i < NU; ++i) { us_prev[i] = us[i]; us_new[i] = ss_ok ? wss[NX + i] : us_prev[i]; }
+    __syncwarp();
     const double* xi = L.xi + (size_t)inst * NXI;
     double* pr = L.par + (size_t)inst * NPAR;
-    for (int i = 0; i < NX; ++i) { pr[MPCB_OFF_X0 + i] = xi[i]; pr[MPCB_OFF_XS + i] = xs[i]; }
-    for (int i = 0; i < NU; ++i) { pr[MPCB_OFF_US + i] = us[i]; pr[MPCB_OFF_UM1 + i] = L.u[(size_t)inst * NU + i]; }
-    for (int i = 0; i < ND; ++i) pr[MPCB_OFF_D + i] = (NXI > NX) ? xi[NX + i] : 0.0;
-    pr[MPCB_OFF_T] = t[inst];
-    for (int i = 0; i < NY * NU; ++i) pr[MPCB_OFF_LAM + i] = 0.0;
-    for (int i = 0; i < NPX * NH; ++i) pr[MPCB_OFF_PX + i] = px ? px[(size_t)inst * NPX * NH + i] : 0.0;
-    for (int i = 0; i < NPY * NH; ++i) pr[MPCB_OFF_PY + i] = py ? py[(size_t)inst * NPY * NH + i] : 0.0;
-    double* wg = L.wguess + (size_t)inst * NW; double* w = L.w + (size_t)inst * NW;
-    if (first) {
-        for (int k = 0; k <= NH; ++k) {
-            for (int i = 0; i < NX; ++i) wg[k * NZ + i] = L.x0m[(size_t)inst * NX + i];
-            if (k < NH) for (int i = 0; i < NU; ++i) wg[k * NZ + NX + i] = L.u0[(size_t)inst * NU + i];
-        }
-    } else if (L.dyn_status[inst] != 2) {
-        const double* wo = L.wopt + (size_t)inst * NW;
-        for (int i = 0; i < NW - NZ; ++i) wg[i] = wo[NZ + i];
-        for (int i = 0; i < NU; ++i) wg[NW - NZ + i] = us_prev[i];
-        for (int i = 0; i < NX; ++i) wg[NW - NX + i] = xs_prev[i];
+    if (lane == 0) {
+        for (int i = 0; i < NX; ++i) { xs[i] = xs_new[i]; xs_out[(size_t)inst * NX + i] = xs_new[i]; }
+        for (int i = 0; i < NU; ++i) { us[i] = us_new[i]; us_out[(size_t)inst * NU + i] = us_new[i]; }
+        for (int i = 0; i < NX; ++i) { pr[MPCB_OFF_X0 + i] = xi[i]; pr[MPCB_OFF_XS + i] = xs_new[i]; }
+        for (int i = 0; i < NU; ++i) { pr[MPCB_OFF_US + i] = us_new[i]; pr[MPCB_OFF_UM1 + i] = L.u[(size_t)inst * NU + i]; }
+        for (int i = 0; i < ND; ++i) pr[MPCB_OFF_D + i] = (NXI > NX) ? xi[NX + i] : 0.0;
+        pr[MPCB_OFF_T] = t[inst];
+        for (int i = 0; i < NY * NU; ++i) pr[MPCB_OFF_LAM + i] = 0.0;
     }
-    for (int i = 0; i < NW; ++i) w[i] = wg[i];
+    for (int i = lane; i < NPX * NH; i += 32) pr[MPCB_OFF_PX + i] = px ? px[(size_t)inst * NPX * NH + i] : 0.0;
+    for (int i = lane; i < NPY * NH; i += 32) pr[MPCB_OFF_PY + i] = py ? py[(size_t)inst * NPY * NH + i] : 0.0;
+    double* wg = L.wguess + (size_t)inst * NW; double* w = L.w + (size_t)inst * NW;
+    const double* wo = L.wopt + (size_t)inst * NW;
+    const bool shift = !first && L.dyn_status[inst] != 2;
+    for (int i = lane; i < NW; i += 32) {
+        double v;
+        if (first) {
+            const int r = i % NZ;
+            v = (r < NX) ? L.x0m[(size_t)inst * NX + r] : L.u0[(size_t)inst * NU + r - NX];
+        } else if (shift) {
+            if (i < NW - NZ) v = wo[NZ + i];
+            else {
+                v = 0.0;
+#pragma unroll
+                for (int j = 0; j < NU; ++j) if (i == NW - NZ + j) v = us_prev[j];
+#pragma unroll
+                for (int j = 0; j < NX; ++j) if (i == NW - NX + j) v = xs_prev[j];
+            }
+        } else {
+            v = wg[i];
+        }
+        wg[i] = v; w[i] = v;
+    }
 }
 
-// after the OCP: status gate, u_k and x(k+1|k) extraction or model fallback (:786-805)
+// after the OCP: status gate, u_k and x(k+1|k) extraction or model fallback (:786-805); one warp per instance
 __global__ void k_step_post(int B, const double* t, const int* status, LoopState L, double* u_out) {
-    const int inst = blockIdx.x * blockDim.x + threadIdx.x;
+    const int inst = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (inst >= B) return;
     double* xi = L.xi + (size_t)inst * NXI; double* u = L.u + (size_t)inst * NU;
     const double* w = L.w + (size_t)inst * NW;
     const int st = status[inst];
-    L.dyn_status[inst] = st;
+    if (lane == 0) L.dyn_status[inst] = st;
     if (st != 2) {
         double* wo = L.wopt + (size_t)inst * NW;
-        for (int i = 0; i < NW; ++i) wo[i] = w[i];
-        for (int i = 0; i < NU; ++i) u[i] = w[NX + i];
-        for (int i = 0; i < NX; ++i) xi[i] = w[NZ + i];
-    } else {
+        for (int i = lane; i < NW; i += 32) wo[i] = w[i];
+        for (int i = lane; i < NU; i += 32) { const double v = w[NX + i]; u[i] = v; u_out[(size_t)inst * NU + i] = v; }
+        for (int i = lane; i < NX; i += 32) xi[i] = w[NZ + i];
+    } else if (lane == 0) {
         double x[NX], ul[NU], d[ND + 1], pxl[NPX + 1], xn[NX];
         for (int i = 0; i < NX; ++i) x[i] = xi[i];
-        for (int i = 0; i < NU; ++i) ul[i] = u[i];
+        for (int i = 0; i < NU; ++i) { ul[i] = u[i]; u_out[(size_t)inst * NU + i] = ul[i]; }
         for (int i = 0; i < ND; ++i) d[i] = (NXI > NX) ? xi[NX + i] : 0.0;
         for (int i = 0; i < NPX; ++i) pxl[i] = L.px0[(size_t)inst * NPX + i];
         dyn_value(x, ul, d, pxl, t[inst], xn);
         for (int i = 0; i < NX; ++i) xi[i] = xn[i];
     }
-    for (int i = 0; i < NU; ++i) u_out[(size_t)inst * NU + i] = u[i];
 }
 #endif
 
@@ -714,11 +725,11 @@ int mpcb_step(mpcb_handle_t h, int est_type, const double* y_meas, const double*
     k_step_pre<<<g, 128, 0, s>>>(B, t, sp, L, xhat_out, dhat_out); launches++;
     rc = mpcb_target(h, L.parss, L.wss, L.fss, L.ss_status, L.ss_iters, s); launches++;
     if (rc) return rc;
-    k_step_mid<<<g, 128, 0, s>>>(B, h->loop_first, t, px, py, L, xs_out, us_out); launches++;
+    k_step_mid<<<nblk((long)B * 32, 128), 128, 0, s>>>(B, h->loop_first, t, px, py, L, xs_out, us_out); launches++;
     rc = mpcb_ocp(h, L.par, L.w, f_dyn, status_dyn, iters_dyn, s);
     if (rc) return rc;
     launches += h->last_launches;
-    k_step_post<<<g, 128, 0, s>>>(B, t, status_dyn, L, u_out); launches++;
+    k_step_post<<<nblk((long)B * 32, 128), 128, 0, s>>>(B, t, status_dyn, L, u_out); launches++;
     if (status_ss) CK(cudaMemcpyAsync(status_ss, L.ss_status, sizeof(int) * B, cudaMemcpyDeviceToDevice, s));
     CK(cudaGetLastError());
     h->kernel_launches[KC_OTHER] += 4;

@@ -469,13 +469,17 @@ MPCB_HD void ocp_eval_stage(OcpInst& I, const OcpShared& S, int k) {
 #ifndef MPCB_KKT_LANES
 #  define MPCB_KKT_LANES 32
 #endif
-#if defined(__CUDA_ARCH__) && (MPCB_KKT_LANES == 32)
-#  define LANE_ID   ((int)(threadIdx.x & 31))
-#  define N_LANES   32
-#  define W_SYNC()  __syncwarp()
-#  define W_SUM(v)  warp_sum(v)
-#  define W_MAX(v)  warp_max(v)
-#  define W_MIN(v)  warp_min(v)
+// MPCB_KKT_LANES may be any power of two <= 32: with L < 32 a warp carries 32/L instances ("lane groups"); the stage
+// blocks of small systems (Ex_NMPC: 3 x 5) leave most of 32 lanes idle, and the kernel is bound by issue slots.
+#if defined(__CUDA_ARCH__) && (MPCB_KKT_LANES > 1)
+#  define LANE_ID    ((int)(threadIdx.x & (MPCB_KKT_LANES - 1)))
+#  define N_LANES    MPCB_KKT_LANES
+#  define GROUP_MASK (MPCB_KKT_LANES == 32 ? 0xffffffffu : (((1u << (MPCB_KKT_LANES & 31)) - 1u) << ((threadIdx.x & 31) & ~(MPCB_KKT_LANES - 1))))
+#  define W_SYNC()   __syncwarp(GROUP_MASK)
+#  define W_SUM(v)   group_sum<MPCB_KKT_LANES>(v, GROUP_MASK)
+#  define W_MAX(v)   group_max<MPCB_KKT_LANES>(v, GROUP_MASK)
+#  define W_MIN(v)   group_min<MPCB_KKT_LANES>(v, GROUP_MASK)
+#  define KKT_ON_LANES 1
 #else
 #  define LANE_ID   0
 #  define N_LANES   1
@@ -483,12 +487,14 @@ MPCB_HD void ocp_eval_stage(OcpInst& I, const OcpShared& S, int k) {
 #  define W_SUM(v)  (v)
 #  define W_MAX(v)  (v)
 #  define W_MIN(v)  (v)
+#  define KKT_ON_LANES 0
 #endif
+#define KKT_STAGED (MPCB_KKT_LANES > 1)        // records staged through the scratch (lane mappings) or read in place
 
 // scratch (doubles): shared memory per warp with 32 lanes, thread-local (registers) with one lane
 struct KktScratch {
     static constexpr int R = 0;                                     // staged record (32-lane mapping only)
-    static constexpr int P = R + (MPCB_KKT_LANES == 32 ? REC_SZ : 0);   // NXA x NXA  cost-to-go Hessian of the next stage
+    static constexpr int P = R + (KKT_STAGED ? REC_SZ : 0);   // NXA x NXA  cost-to-go Hessian of the next stage
     static constexpr int p = P + NXA * NXA;             // NXA
     static constexpr int M = p + NXA;                  // NZA x NZA  condensed stage Hessian
     static constexpr int q = M + NZA * NZA;             // NZA
@@ -498,7 +504,7 @@ struct KktScratch {
     static constexpr int kk = K + NU * NXA;            // NU
     static constexpr int cf = kk + NU;                // NGS      slack gradient coefficient
     static constexpr int F = cf + NGS;                // staged forward record (32-lane mapping only)
-    static constexpr int dx = F + (MPCB_KKT_LANES == 32 ? FREC_SZ : 0);   // NXA
+    static constexpr int dx = F + (KKT_STAGED ? FREC_SZ : 0);   // NXA
     static constexpr int du = dx + NXA;                // NU
     static constexpr int dxn = du + NU;               // NXA
     static constexpr int total = dxn + NXA;
@@ -509,25 +515,25 @@ struct KktScratch {
 // only copied to shared memory when its turn comes: the DRAM/L2 latency of the load overlaps the arithmetic
 // (ncu before this: 54 % of the kernel's stall samples sat on the record copy).  With one lane the record is read in
 // place.
-#define REC_PER_LANE ((R_PART + 31) / 32)
+#define REC_PER_LANE ((R_PART + MPCB_KKT_LANES - 1) / MPCB_KKT_LANES)
 struct RecStream {
     double pre[REC_PER_LANE];
 };
 MPCB_HD void rec_prefetch(RecStream& rs, const double* rk) {
-#if defined(__CUDA_ARCH__) && (MPCB_KKT_LANES == 32)
+#if KKT_ON_LANES
 #pragma unroll
-    for (int q = 0; q < REC_PER_LANE; ++q) { const int e = LANE_ID + 32 * q; rs.pre[q] = (e < R_PART) ? rk[e] : 0.0; }
+    for (int q = 0; q < REC_PER_LANE; ++q) { const int e = LANE_ID + N_LANES * q; rs.pre[q] = (e < R_PART) ? rk[e] : 0.0; }
 #else
     (void)rs; (void)rk;
 #endif
 }
 // publish the prefetched record (must be the one of `rk`) and start fetching `rk_next` (may be null)
 MPCB_HD const double* stage_record(RecStream& rs, const double* rk, const double* rk_next, double* sm) {
-#if defined(__CUDA_ARCH__) && (MPCB_KKT_LANES == 32)
+#if KKT_ON_LANES
     double* R = sm + KktScratch::R;
     W_SYNC();
 #pragma unroll
-    for (int q = 0; q < REC_PER_LANE; ++q) { const int e = LANE_ID + 32 * q; if (e < R_PART) R[e] = rs.pre[q]; }
+    for (int q = 0; q < REC_PER_LANE; ++q) { const int e = LANE_ID + N_LANES * q; if (e < R_PART) R[e] = rs.pre[q]; }
     if (rk_next) rec_prefetch(rs, rk_next);
     W_SYNC();
     return R;
@@ -761,28 +767,28 @@ MPCB_HD void ocp_kkt(OcpInst& I, const OcpShared& S, double* sm) {
     //      one stage ahead, one double per lane)
     double* dxa = sm + KktScratch::dx; double* du = sm + KktScratch::du; double* dxb = sm + KktScratch::dxn;
     for (int i = lane; i < NXA; i += N_LANES) { dxa[i] = 0.0; I.dw[i] = 0.0; }
-#if defined(__CUDA_ARCH__) && (MPCB_KKT_LANES == 32)
+#if KKT_ON_LANES
     constexpr int NHEAD = R_C + NXA, NFH = FREC_P;              // doubles needed per stage: record head, forward-record head
-    constexpr int HPL = (NHEAD + NFH + 31) / 32;
+    constexpr int HPL = (NHEAD + NFH + N_LANES - 1) / N_LANES;
     double* Rs = sm + KktScratch::R;                            // staged: [record head | forward-record head]
     double hpre[HPL];
 #pragma unroll
     for (int q = 0; q < HPL; ++q) {
-        const int e = lane + 32 * q;
+        const int e = lane + N_LANES * q;
         hpre[q] = (e < NHEAD) ? I.rec[e] : ((e < NHEAD + NFH) ? I.frec[e - NHEAD] : 0.0);
     }
 #endif
     W_SYNC();
     for (int k = 0; k < NH; ++k) {
         double* dx = (k & 1) ? dxb : dxa; double* dxn = (k & 1) ? dxa : dxb;
-#if defined(__CUDA_ARCH__) && (MPCB_KKT_LANES == 32)
+#if KKT_ON_LANES
 #pragma unroll
-        for (int q = 0; q < HPL; ++q) { const int e = lane + 32 * q; if (e < NHEAD + NFH) Rs[e] = hpre[q]; }
+        for (int q = 0; q < HPL; ++q) { const int e = lane + N_LANES * q; if (e < NHEAD + NFH) Rs[e] = hpre[q]; }
         if (k + 1 < NH) {
             const double* rn = I.rec + (k + 1) * REC_SZ; const double* fn = I.frec + (k + 1) * FREC_SZ;
 #pragma unroll
             for (int q = 0; q < HPL; ++q) {
-                const int e = lane + 32 * q;
+                const int e = lane + N_LANES * q;
                 hpre[q] = (e < NHEAD) ? rn[e] : ((e < NHEAD + NFH) ? fn[e - NHEAD] : 0.0);
             }
         }
@@ -950,6 +956,7 @@ MPCB_HD void ocp_trial_stage(OcpInst& I, const OcpShared& S, int k) {
 #undef W_SUM
 #undef W_MAX
 #undef W_MIN
+#undef GROUP_MASK
 #ifdef __CUDA_ARCH__
 #  define LANE_ID   ((int)(threadIdx.x & 31))
 #  define N_LANES   32
