@@ -274,7 +274,7 @@ __global__ void k_step_mid(int B, int first, const double* t, const double* px, 
     for (int i = lane; i < NPY * NH; i += 32) pr[MPCB_OFF_PY + i] = py ? py[(size_t)inst * NPY * NH + i] : 0.0;
     double* wg = L.wguess + (size_t)inst * NW; double* w = L.w + (size_t)inst * NW;
     const double* wo = L.wopt + (size_t)inst * NW;
-    const bool shift = !first && L.dyn_status[inst] != 2;
+    const bool shift = !first && L.dyn_status[inst] != 2 && L.dyn_status[inst] != -13;
     for (int i = lane; i < NW; i += 32) {
         double v;
         if (first) {
@@ -304,7 +304,9 @@ __global__ void k_step_post(int B, const double* t, const int* status, LoopState
     const double* w = L.w + (size_t)inst * NW;
     const int st = status[inst];
     if (lane == 0) L.dyn_status[inst] = st;
-    if (st != 2) {
+    if (st == -13) {                                      // diverged instance (NaN state): frozen, u keeps its value
+        for (int i = lane; i < NU; i += 32) u_out[(size_t)inst * NU + i] = u[i];
+    } else if (st != 2) {
         double* wo = L.wopt + (size_t)inst * NW;
         for (int i = lane; i < NW; i += 32) wo[i] = w[i];
         for (int i = lane; i < NU; i += 32) { const double v = w[NX + i]; u[i] = v; u_out[(size_t)inst * NU + i] = v; }

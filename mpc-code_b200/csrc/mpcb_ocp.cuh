@@ -208,6 +208,11 @@ MPCB_HD void ocp_init_stage(OcpInst& I, const OcpShared& S, int k) {
         st.mu = S.o.mu_init; st.tau = fmax(0.99, 1.0 - S.o.mu_init);
         st.alpha = st.alpha_z = 0.0; st.theta0 = -1.0; st.dw_last = 0.0; st.fval = 0.0; st.E0 = 0.0;
         st.state = ST_EVAL; st.iter = 0; st.status = -1; st.nfilt = 0; st.acc_cnt = 0; st.ls_iter = 0;
+        // a non-finite estimate / target / disturbance (diverged instance) cannot be evaluated: IPOPT's
+        // Invalid_Number_Detected (-13), decided here so that the instance does not burn line-search ticks
+        double chk = 0.0;
+        for (int i = 0; i < MPCB_OFF_LAM; ++i) chk += I.par[i];
+        if (!(chk == chk) || !fin(chk)) { st.state = ST_DONE; st.status = -13; }
     }
     // state part z_k = [x_k; v_k]
     for (int i = 0; i < NXA; ++i) {

@@ -182,6 +182,12 @@ MPCB_HD void tgt_solve(const double* par, double* w, double* fout, int* status_o
     double filt[2 * MPCB_MAXFILT]; int nfilt = 0, acc = 0, it = 0, status = -1;
     double f, c[MCS], grad[NWS], J[MCS * NWS], Hp[NWSP];
     tgt_eval(w, par, y, true, &f, c, grad, J, Hp);
+    {   // IPOPT: a starting point whose functions do not evaluate ends the solve with Invalid_Number_Detected (-13)
+        double chk = f;
+        for (int i = 0; i < MCS; ++i) chk += c[i];
+        for (int i = 0; i < NWS; ++i) chk += grad[i];
+        if (!(chk == chk) || !fin(chk)) { *fout = f; *status_out = -13; *iters_out = 0; return; }
+    }
     while (true) {
         // optimality error
         double dual = 0.0, prim = 0.0, ysum = 0.0, zsum = 0.0, c0 = 0.0;

@@ -275,6 +275,7 @@ class BatchedMpc:
             self._sp = row(np.concatenate([usp, ysp, xsp])); self._sp_key = sp_key
         o = h.step(self.est_type, y_meas, tt, self._sp, px, py)
         self.u_k = o["u"]
+        self.dead |= o["status"] == -13          # Invalid_Number_Detected: diverged instance, frozen (MPC_code.py:671-673 exits)
         out.update(U=o["u"], X_CORR=o["xhat"], D_HAT=o["dhat"], XS=o["xs"], US=o["us"], F_DYN=o["f"],
                    STATUS_DYN=o["status"], ITER_DYN=o["iters"], STATUS_SS=o["status_ss"])
         if simulate:

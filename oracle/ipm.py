@@ -340,6 +340,8 @@ def solve_nlp(n: int, m: int, fun: Callable, x0, xL, xU, gL, gU, opts: Optional[
             th_t = np.abs(ev_t["C"]).sum()
             ph_t = barrier(ev_t["f"], vt)
             ok = np.isfinite(th_t) and np.isfinite(ph_t) and th_t <= theta_max
+            if o.verbose and o.verbose > 1:
+                print("      trial alpha %.3e theta_t %.9e (theta %.9e) phi_t %.9e (phi %.9e)" % (alpha, th_t, theta, ph_t, phi))
             if ok:
                 for (tf_, pf_) in filt:
                     if th_t >= tf_ and ph_t >= pf_:
