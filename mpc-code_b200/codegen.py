@@ -182,7 +182,7 @@ def live_nodes(roots, cut_nodes, cut_recips):
     return live
 
 
-def expensive_entries(consumers, tainted, shared_reciprocals=True):
+def expensive_entries(consumers, tainted, shared_reciprocals=True, recips=True):
     """Expensive sub-expressions (transcendentals, reciprocals of non-constant denominators) of the output lists in
     ``consumers`` that do not depend on the symbols in ``tainted`` - i.e. that a producer evaluated at the same point
     can compute once and pass on.  Entries that end up unused once the others are cut are dropped."""
@@ -196,7 +196,7 @@ def expensive_entries(consumers, tainted, shared_reciprocals=True):
     for n in order:
         if n.op in EXPENSIVE_OPS and not dep[n.uid] and any(a.op != "const" for a in n.args):
             entries.append(("node", n))
-        if shared_reciprocals and n.op == "div":
+        if shared_reciprocals and recips and n.op == "div":
             den = n.args[1]
             if den.op != "const" and not dep[den.uid] and den.uid not in seen_den:
                 seen_den.add(den.uid)

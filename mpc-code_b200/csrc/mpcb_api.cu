@@ -631,6 +631,9 @@ int mpcb_plant_step(mpcb_handle_t h, double* x, const double* u, const double* t
 
 int mpcb_set_profiling(mpcb_handle_t h, int on) {
     h->profile = on ? 1 : 0;
+    // events are created here, not inside a timed region (cudaEventCreate occasionally takes milliseconds when the
+    // driver grows its pool: seen as 20-100 ms outliers on the steps that set a new record of launches)
+    if (on) while (h->ev_pool.size() < 2 * 1024) { cudaEvent_t e; if (cudaEventCreate(&e) != cudaSuccess) break; h->ev_pool.push_back(e); }
     for (int i = 0; i < MPCB_NKERNELS; ++i) { h->kernel_ms[i] = 0.0; h->kernel_launches[i] = 0; }
     h->eval_instances = h->trial_instances = 0;
     cudaMemset(h->counters, 0, 2 * sizeof(unsigned long long));

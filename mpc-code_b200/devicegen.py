@@ -36,7 +36,12 @@ def _cached_variants(prefix: str, base, f, vjp_in, vjp_out, sh_in, sh_out, taint
     the same stage points, so transcendentals and reciprocals of the right-hand side are evaluated once per point
     instead of three times.  Empty when the right-hand side has nothing expensive to share."""
     consumers = [[e for _, o in vjp_out for e in SX(o).elements()], [e for _, o in sh_out for e in SX(o).elements()]]
-    entries = expensive_entries(consumers, tainted)
+    # Measured on B200 (Ex_NMPC, profiles/r01_v11_*): caching exp AND the two reciprocals (3 doubles per stage point)
+    # cuts the kernel's instructions by 28 % but doubles its DRAM traffic (the per-thread stage buffer grows from 960 to
+    # 1 920 B and no longer stays in L2): 0.317 -> 0.298 ms per launch.  Caching the transcendental only (1 280 B):
+    # 0.277 ms.  So reciprocals (~10 instructions) are recomputed; MPCB_CACHE_RECIPS=1 restores the larger cache.
+    import os
+    entries = expensive_entries(consumers, tainted, recips=os.environ.get("MPCB_CACHE_RECIPS", "0") == "1")
     if not entries:
         return []
     return [CFunction(prefix + "f_c", base, [("xdot", f), ("cache", cache_expressions(entries))]),
