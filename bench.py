@@ -26,6 +26,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 BATCH_PER_GPU = 4096
+DEFAULT_GROUPS = 8         # instance groups of the fused step (mpcb_set_groups); MPCB_GROUPS overrides
 SEED_X0, SEED_NOISE = 20240419, 7
 X0_SCALE = np.array([0.02, 0.002, 0.02])
 METRIC = "batched MPC steps/sec (Ex_NMPC CSTR, N=50, FP64)"
@@ -223,9 +224,12 @@ def run_gpu(args):
     ys = torch.empty(total, B, prob.ny, device=dev, dtype=torch.float64)
     us = torch.empty(total, B, prob.nu, device=dev, dtype=torch.float64)
     st_dyn = torch.empty(K, B, device=dev, dtype=torch.int32); it_dyn = torch.empty_like(st_dyn); st_ss = torch.empty_like(st_dyn)
+    # one host thread per group spins on its stream: leave two cores per thread, never more than DEFAULT_GROUPS
+    cores_here = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    groups = int(os.environ.get("MPCB_GROUPS", max(1, min(DEFAULT_GROUPS, cores_here // (2 * world)))))
+    ctl.h.set_groups(groups)
     for k in range(W):
         o = ctl.step_fused(noise_dev[k]); ys[k].copy_(o["Yp"]); us[k].copy_(o["U"])
-    ctl.h.set_profiling(not os.environ.get("MPCB_BENCH_NOPROF"))
     launches0 = ctl.h.launches
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
     barrier()
@@ -239,8 +243,6 @@ def run_gpu(args):
     barrier()
     windows.append((t_w0, time.time()))
     elapsed_ms = ev[0].elapsed_time(ev[K])
-    prof = ctl.h.profile()
-    ctl.h.set_profiling(False)
     launches = ctl.h.launches - launches0
     step_ms = np.array([ev[k].elapsed_time(ev[k + 1]) for k in range(K)])
     t_all = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
@@ -248,6 +250,23 @@ def run_gpu(args):
         dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
     elapsed_max = float(t_all.item())
     value = world * B * K / (elapsed_max * 1e-3)
+
+    # ---------------- kernel timing: the same W+K steps replayed WITHOUT groups and with event brackets around every launch
+    # (with groups the kernels of different groups overlap and a per-kernel duration is not attributable) ----------------
+    ctl.h.set_groups(1)
+    ctl.reset(x0_p=x0, x0_m=x0)
+    for k in range(W):
+        ctl.step_fused(noise_dev[k])
+    ctl.h.set_profiling(True)
+    barrier()
+    t_w0 = time.time()
+    for k in range(K):
+        ctl.step_fused(noise_dev[W + k])
+    barrier()
+    windows.append((t_w0, time.time()))
+    prof = ctl.h.profile()
+    ctl.h.set_profiling(False)
+    ctl.h.set_groups(groups)
 
     # ---------------- end to end through the public API with host buffers (e2e) ----------------
     y_host = ys.cpu().pin_memory()                      # recorded plant measurements, [W+K, B, ny]
@@ -302,9 +321,17 @@ def run_gpu(args):
     hbm_peak, hbm_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback")
     ach_tf = evals * f_stage / eval_s / 1e12 if eval_s > 0 else 0.0
     ach_gb = evals * b_stage / eval_s / 1e9 if eval_s > 0 else 0.0
+    traffic, traffic_src = None, None
+    try:        # DRAM bytes of the kernel from the committed ncu capture, scaled to the average launch of THIS run
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["k_ocp_eval"]
+        traffic = tr["dram_bytes_per_full_launch"] / tr["stage_evals_per_full_launch"] * evals / max(kl["ocp_eval"], 1)
+        traffic_src = tr["source"]
+    except Exception:
+        pass
     roofline = {
         "kernel": "k_ocp_eval", "bound": "fp64", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
-        "frac": ach_tf / fp64_peak if fp64_peak else None, "traffic": None,
+        "frac": ach_tf / fp64_peak if fp64_peak else None, "traffic": traffic, "traffic_unit": "bytes per launch (average launch)",
+        "traffic_source": traffic_src, "algorithmic_bytes_per_launch": b_stage * evals / max(kl["ocp_eval"], 1),
         "peak_source": "FP64 FMA micro-benchmark run in this process (mpcb_dfma_peak); MEASURED_PEAKS.json has no FP64 entry",
         "flops_per_stage_eval": f_stage, "stage_evals": int(evals), "kernel_ms_total": kms["ocp_eval"],
         "kernel_launches": kl["ocp_eval"], "avg_launch_ms": kms["ocp_eval"] / max(kl["ocp_eval"], 1),
@@ -331,6 +358,7 @@ def run_gpu(args):
         "config": {"workload": "Ex_NMPC (configs[1]): CSTR NMPC + EKF + target, N=50, Mx=10, closed loop with plant and "
                                "measurement noise; %d instances per GPU, x0 perturbed 2%%/0.2%%/2%% (seed %d)" % (B, SEED_X0),
                    "batch_per_gpu": B, "global_batch": world * B, "parallelism": "instances sharded, %d rank(s)" % world,
+                   "instance_groups_per_gpu": groups,
                    "cache": "per-step working set %.0f MB per GPU > 126 MB L2 (no flush needed)" % (B * cp_ws_bytes(cp) / 1e6)},
         "p50_step_latency_ms": float(np.median(step_ms)), "p99_step_latency_ms": float(np.percentile(step_ms, 99)),
         "slowest_steps": [[int(i), float(step_ms[i])] for i in np.argsort(-step_ms)[:3]],

@@ -134,6 +134,13 @@ int  mpcb_step(mpcb_handle_t h, int est_type, const double* y_meas, const double
                double* f_dyn, int* status_dyn, int* iters_dyn, int* status_ss, void* stream);
 int  mpcb_loop_get(mpcb_handle_t h, double* xi, double* P, double* u, void* stream);
 
+/* Instance groups of the fused step: mpcb_step cuts the batch into n contiguous groups, each driven by its own host
+ * thread and CUDA stream, so that the latency-bound phases of one group (Riccati sweep, target solve, the tail of
+ * iterations in which few instances are still active) overlap the evaluation kernels of another.  Results do not
+ * change (instances are independent - the reference solves them one after another, MPC_code.py:485).  With n > 1
+ * mpcb_step returns with all outputs complete.  Default 1. */
+int  mpcb_set_groups(mpcb_handle_t h, int n);
+
 /* Profiling.  With profiling on, every kernel launch is bracketed by CUDA events on its stream and the
  * time is accumulated per kernel class: 0 ocp_init, 1 ocp_eval (stage derivatives), 2 ocp_kkt (Riccati
  * step), 3 ocp_trial (line-search evaluation), 4 ocp_accept, 5 target, 6 estimate, 7 other.

@@ -5,7 +5,10 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <string.h>
+#include <condition_variable>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 #include "mpcb.h"
@@ -346,6 +349,21 @@ struct mpcb_ctx {
     unsigned long long eval_instances, trial_instances;
     std::vector<cudaEvent_t> ev_pool;
     std::vector<std::pair<int, int>> ev_pending;   // (kernel class, index of start event; stop = +1)
+    // instance groups of the fused step (mpcb_set_groups): sub-batches driven by their own host thread and stream
+    int ngroups;
+    std::vector<struct StepGroup*> groups;
+    cudaEvent_t ev_in;
+};
+
+struct StepArgs {
+    int est_type; const double *y_meas, *t, *sp, *px, *py;
+    double *u_out, *xhat_out, *dhat_out, *xs_out, *us_out, *f_dyn; int *status_dyn, *iters_dyn, *status_ss;
+};
+struct StepGroup {
+    mpcb_ctx* c; int b0, nb; cudaStream_t s;
+    std::thread th; std::mutex m; std::condition_variable cv;
+    long job = 0, done = 0; bool quit = false; int rc = 0;
+    StepArgs a;
 };
 
 static IpmOpts to_ipm(const mpcb_opts_t& o) {
@@ -457,12 +475,17 @@ int mpcb_create(int batch, const mpcb_opts_t* oss, const mpcb_opts_t* odyn, mpcb
     CK(cudaMemset(h->counters, 0, 2 * sizeof(unsigned long long)));
     h->loop_mem = nullptr; h->loop_imem = nullptr; h->loop_first = 1;
     h->profile = 0; h->eval_instances = h->trial_instances = 0;
+    h->ngroups = 1; h->ev_in = nullptr;
     for (int i = 0; i < MPCB_NKERNELS; ++i) { h->kernel_ms[i] = 0.0; h->kernel_launches[i] = 0; }
     return 0;
 }
 
+static void groups_teardown(mpcb_ctx* h);
+
 int mpcb_destroy(mpcb_handle_t h) {
     if (!h) return 0;
+    groups_teardown(h);
+    if (h->ev_in) cudaEventDestroy(h->ev_in);
     cudaFree(h->ws); cudaFree(h->st); cudaFree(h->lbx); cudaFree(h->ubx); cudaFree(h->lbg); cudaFree(h->ubg);
     cudaFree(h->ss_lbx); cudaFree(h->ss_ubx); cudaFree(h->Qkf); cudaFree(h->Rkf); cudaFree(h->Kest);
     cudaFree(h->dmin); cudaFree(h->dmax); cudaFree(h->n_active); cudaFreeHost(h->h_active); cudaFree(h->counters);
@@ -637,12 +660,24 @@ int mpcb_set_profiling(mpcb_handle_t h, int on) {
     for (int i = 0; i < MPCB_NKERNELS; ++i) { h->kernel_ms[i] = 0.0; h->kernel_launches[i] = 0; }
     h->eval_instances = h->trial_instances = 0;
     cudaMemset(h->counters, 0, 2 * sizeof(unsigned long long));
+    for (StepGroup* g : h->groups) {
+        mpcb_ctx* c = g->c;
+        c->profile = h->profile;
+        for (int i = 0; i < MPCB_NKERNELS; ++i) { c->kernel_ms[i] = 0.0; c->kernel_launches[i] = 0; }
+        c->eval_instances = c->trial_instances = 0;
+        cudaMemset(c->counters, 0, 2 * sizeof(unsigned long long));
+        if (on) while (c->ev_pool.size() < 2 * 1024) { cudaEvent_t e; if (cudaEventCreate(&e) != cudaSuccess) break; c->ev_pool.push_back(e); }
+    }
     return 0;
 }
 
 int mpcb_get_profile(mpcb_handle_t h, double* kernel_ms, long* kernel_launches, unsigned long long* instance_counts) {
     for (int i = 0; i < MPCB_NKERNELS; ++i) { kernel_ms[i] = h->kernel_ms[i]; kernel_launches[i] = h->kernel_launches[i]; }
     instance_counts[0] = h->eval_instances; instance_counts[1] = h->trial_instances;
+    for (StepGroup* g : h->groups) {        // grouped steps: sums over the groups (their kernels overlap in time)
+        for (int i = 0; i < MPCB_NKERNELS; ++i) { kernel_ms[i] += g->c->kernel_ms[i]; kernel_launches[i] += g->c->kernel_launches[i]; }
+        instance_counts[0] += g->c->eval_instances; instance_counts[1] += g->c->trial_instances;
+    }
     return 0;
 }
 
@@ -715,7 +750,7 @@ int mpcb_loop_get(mpcb_handle_t h, double* xi, double* P, double* u, void* strea
 #endif
 }
 
-int mpcb_step(mpcb_handle_t h, int est_type, const double* y_meas, const double* t, const double* sp, const double* px,
+static int step_impl(mpcb_ctx* h, int est_type, const double* y_meas, const double* t, const double* sp, const double* px,
               const double* py, double* u_out, double* xhat_out, double* dhat_out, double* xs_out, double* us_out,
               double* f_dyn, int* status_dyn, int* iters_dyn, int* status_ss, void* stream) {
 #if MPCB_HAS_OCP && MPCB_HAS_TARGET
@@ -741,6 +776,123 @@ int mpcb_step(mpcb_handle_t h, int est_type, const double* y_meas, const double*
     h->loop_first = 0;
     h->last_launches = launches;
     return 0;
+#else
+    h->err = "library built without OCP/target"; return -3;
+#endif
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Instance groups.  The solve alternates throughput-bound kernels (stage derivatives) with latency-bound ones (the
+// N-sequential Riccati sweep, the one-thread-per-instance target solve, the tail of ticks in which only a few
+// instances still iterate).  Instances are independent, so the batch can be cut into G contiguous groups, each
+// driven by its own host thread on its own stream: one group's latency-bound phase overlaps another's evaluation.
+// Results are bit-identical to the ungrouped step.  Children alias the parent's buffers at an instance offset.
+// ---------------------------------------------------------------------------------------------
+#if MPCB_HAS_OCP && MPCB_HAS_TARGET
+static void group_worker(StepGroup* g) {
+    cudaSetDevice(g->c->device);
+    std::unique_lock<std::mutex> lk(g->m);
+    while (true) {
+        g->cv.wait(lk, [g] { return g->quit || g->job > g->done; });
+        if (g->quit) return;
+        lk.unlock();
+        const StepArgs& a = g->a;
+        int rc = step_impl(g->c, a.est_type, a.y_meas, a.t, a.sp, a.px, a.py, a.u_out, a.xhat_out, a.dhat_out, a.xs_out,
+                           a.us_out, a.f_dyn, a.status_dyn, a.iters_dyn, a.status_ss, g->s);
+        if (cudaStreamSynchronize(g->s) != cudaSuccess && rc == 0) { g->c->err = "cudaStreamSynchronize failed in a group"; rc = -1; }
+        lk.lock();
+        g->rc = rc; g->done = g->job;
+        g->cv.notify_all();
+    }
+}
+
+static int groups_setup(mpcb_ctx* h) {
+    groups_teardown(h);
+    const int G = h->ngroups, B = h->B, per = (B + G - 1) / G;
+    if (!h->ev_in) CK(cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
+    for (int b0 = 0; b0 < B; b0 += per) {
+        StepGroup* g = new StepGroup();
+        g->b0 = b0; g->nb = (b0 + per <= B) ? per : B - b0;
+        mpcb_ctx* c = new mpcb_ctx(*h);                       // constants (bounds, filter matrices) are shared
+        c->groups.clear(); c->ngroups = 1; c->ev_pool.clear(); c->ev_pending.clear(); c->ev_in = nullptr;
+        c->B = g->nb;
+        c->ws = h->ws + (size_t)b0 * OcpLayout::total; c->st = h->st + b0;
+        if (cudaMalloc(&c->n_active, sizeof(int)) != cudaSuccess || cudaMallocHost(&c->h_active, sizeof(int)) != cudaSuccess ||
+            cudaMalloc(&c->counters, 2 * sizeof(unsigned long long)) != cudaSuccess) { h->err = "group allocation failed"; return -1; }
+        cudaMemset(c->counters, 0, 2 * sizeof(unsigned long long));
+        const size_t o = (size_t)b0;
+        LoopState& L = c->L; const LoopState& P = h->L;
+        L.xi = P.xi + o * NXI; L.P = P.P + o * NXI * NXI; L.u = P.u + o * NU; L.us = P.us + o * NU; L.u0 = P.u0 + o * NU;
+        L.xs = P.xs + o * NX; L.x0m = P.x0m + o * NX; L.wguess = P.wguess + o * NW; L.wopt = P.wopt + o * NW; L.w = P.w + o * NW;
+        L.parss = P.parss + o * MPCB_NPARSS; L.wss = P.wss + o * NWS; L.par = P.par + o * NPAR; L.px0 = P.px0 + o * NPX;
+        L.py0 = P.py0 + o * NPY; L.fss = P.fss + o;
+        L.dyn_status = P.dyn_status + o; L.ss_status = P.ss_status + o; L.ss_iters = P.ss_iters + o;
+        g->c = c;
+        if (cudaStreamCreateWithFlags(&g->s, cudaStreamNonBlocking) != cudaSuccess) { h->err = "group stream creation failed"; return -1; }
+        g->th = std::thread(group_worker, g);
+        h->groups.push_back(g);
+    }
+    return 0;
+}
+#endif
+
+static void groups_teardown(mpcb_ctx* h) {
+#if MPCB_HAS_OCP && MPCB_HAS_TARGET
+    for (StepGroup* g : h->groups) {
+        { std::lock_guard<std::mutex> lk(g->m); g->quit = true; }
+        g->cv.notify_all();
+        if (g->th.joinable()) g->th.join();
+        cudaStreamDestroy(g->s);
+        cudaFree(g->c->n_active); cudaFreeHost(g->c->h_active); cudaFree(g->c->counters);
+        for (auto e : g->c->ev_pool) cudaEventDestroy(e);
+        delete g->c; delete g;
+    }
+#endif
+    h->groups.clear();
+}
+
+int mpcb_set_groups(mpcb_handle_t h, int n) {
+    if (n < 1 || n > h->B) { h->err = "mpcb_set_groups: need 1 <= n <= batch"; return -2; }
+    if (n != h->ngroups) { groups_teardown(h); h->ngroups = n; }
+    return 0;
+}
+
+int mpcb_step(mpcb_handle_t h, int est_type, const double* y_meas, const double* t, const double* sp, const double* px,
+              const double* py, double* u_out, double* xhat_out, double* dhat_out, double* xs_out, double* us_out,
+              double* f_dyn, int* status_dyn, int* iters_dyn, int* status_ss, void* stream) {
+#if MPCB_HAS_OCP && MPCB_HAS_TARGET
+    if (h->ngroups <= 1)
+        return step_impl(h, est_type, y_meas, t, sp, px, py, u_out, xhat_out, dhat_out, xs_out, us_out, f_dyn, status_dyn,
+                         iters_dyn, status_ss, stream);
+    if (!h->loop_mem) { h->err = "mpcb_loop_reset has not been called"; return -2; }
+    if (h->groups.empty()) { int rc = groups_setup(h); if (rc) return rc; }
+    CK(cudaEventRecord(h->ev_in, (cudaStream_t)stream));      // the groups start after the caller's work on `stream`
+    for (StepGroup* g : h->groups) {
+        const size_t o = (size_t)g->b0;
+        mpcb_ctx* c = g->c;
+        c->opts_ss = h->opts_ss; c->opts_dyn = h->opts_dyn; c->have_dbounds = h->have_dbounds; c->loop_first = h->loop_first;
+        c->profile = h->profile;
+        CK(cudaStreamWaitEvent(g->s, h->ev_in, 0));
+        StepArgs a;
+        a.est_type = est_type; a.y_meas = y_meas + o * NY; a.t = t + o; a.sp = sp + o * (NU + NY + NX);
+        a.px = px ? px + o * NPX * NH : nullptr; a.py = py ? py + o * NPY * NH : nullptr;
+        a.u_out = u_out + o * NU; a.xhat_out = xhat_out + o * NX; a.dhat_out = dhat_out + o * ND; a.xs_out = xs_out + o * NX;
+        a.us_out = us_out + o * NU; a.f_dyn = f_dyn + o; a.status_dyn = status_dyn + o; a.iters_dyn = iters_dyn + o;
+        a.status_ss = status_ss ? status_ss + o : nullptr;
+        { std::lock_guard<std::mutex> lk(g->m); g->a = a; g->job += 1; }
+        g->cv.notify_all();
+    }
+    int rc = 0, launches = 0, ticks = 0;
+    for (StepGroup* g : h->groups) {
+        std::unique_lock<std::mutex> lk(g->m);
+        g->cv.wait(lk, [g] { return g->done == g->job; });
+        if (g->rc && !rc) { rc = g->rc; h->err = g->c->err; }
+        launches += g->c->last_launches; ticks = ticks > g->c->last_ticks ? ticks : g->c->last_ticks;
+    }
+    // the groups have synchronised their streams: every output is complete when this returns
+    h->loop_first = 0; h->last_launches = launches; h->last_ticks = ticks;
+    return rc;
 #else
     h->err = "library built without OCP/target"; return -3;
 #endif

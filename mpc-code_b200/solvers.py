@@ -34,7 +34,7 @@ class MpcbOpts(ctypes.Structure):
 C_SYMBOLS = ("mpcb_abi_version", "mpcb_default_opts", "mpcb_get_dims", "mpcb_model_flops", "mpcb_create",
              "mpcb_destroy", "mpcb_last_error", "mpcb_set_const", "mpcb_estimate", "mpcb_target", "mpcb_ocp",
              "mpcb_plant_meas", "mpcb_plant_step", "mpcb_model_output", "mpcb_model_step", "mpcb_stage_derivs",
-             "mpcb_last_launches", "mpcb_last_ticks", "mpcb_set_profiling", "mpcb_get_profile", "mpcb_dfma_peak",
+             "mpcb_last_launches", "mpcb_last_ticks", "mpcb_set_groups", "mpcb_set_profiling", "mpcb_get_profile", "mpcb_dfma_peak",
              "mpcb_loop_reset", "mpcb_step", "mpcb_loop_get")
 
 
@@ -65,6 +65,7 @@ class MpcbLibrary:
         L.mpcb_model_step.argtypes = [vp] * 8
         L.mpcb_stage_derivs.argtypes = [vp] * 9
         L.mpcb_last_launches.argtypes = [vp]; L.mpcb_last_ticks.argtypes = [vp]
+        L.mpcb_set_groups.argtypes = [vp, ctypes.c_int]
         L.mpcb_set_profiling.argtypes = [vp, ci]
         L.mpcb_get_profile.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_long),
                                        ctypes.POINTER(ctypes.c_ulonglong)]
@@ -261,6 +262,10 @@ class MpcbHandle:
                                      o["status_ss"].data_ptr(), self._stream()))
         self.launches += self.L.mpcb_last_launches(self._h)
         return o
+
+    def set_groups(self, n: int):
+        """Cut the batch of the fused step into ``n`` instance groups pipelined on separate streams (`mpcb_set_groups`)."""
+        self._check(self.L.mpcb_set_groups(self._h, int(n)))
 
     def loop_state(self):
         """Copies of the device-resident loop state: xi = [x(k+1|k); d], P, u."""

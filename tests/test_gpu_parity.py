@@ -269,3 +269,21 @@ def test_enmpc_full_batch(enmpc):
     sub.reset(x0_p=x0[1000:1032], x0_m=np.tile(p.x0_m, (32, 1)))
     u2 = sub.run(p.Nsim, fused=True)["U"].cpu().numpy()
     assert np.array_equal(u[:, 1000:1032, :], u2)
+
+
+@pytest.mark.parametrize("groups", [2, 3])
+def test_instance_groups_do_not_change_results(nmpc, cp, groups):
+    """`mpcb_set_groups`: sub-batches on their own host threads and streams must reproduce the ungrouped step bit for
+    bit (ragged last group included: 37 instances in 3 groups of 13, 13, 11)."""
+    import torch
+    p = nmpc.prob
+    B, Ns = 37, 8
+    rng = np.random.default_rng(5)
+    x0 = np.tile(p.x0_p, (B, 1)) * (1 + np.array([0.01, 0.001, 0.01]) * rng.uniform(-1, 1, (B, p.nxp)))
+    noise = 3e-4 * rng.standard_normal((Ns, B, p.ny))
+    a = cp.controller(B); a.reset(x0_p=x0, x0_m=x0); ra = a.run(Ns, noise=noise, fused=True)
+    b = cp.controller(B); b.reset(x0_p=x0, x0_m=x0); b.h.set_groups(groups); rb = b.run(Ns, noise=noise, fused=True)
+    for key in ("U", "XS", "US", "D_HAT", "X_HAT", "Xp", "Yp", "F_DYN", "STATUS_DYN", "ITER_DYN", "STATUS_SS"):
+        assert torch.equal(ra[key], rb[key]), key
+    b.h.set_groups(1)                                   # switching back tears the worker threads down
+    b.step_fused(noise[0])
