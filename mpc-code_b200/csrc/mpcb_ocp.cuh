@@ -77,7 +77,7 @@ struct SysCont {
 struct OcpInst {
     double* w; double* wext; const double* par;      // w: internal iterate (NWI); wext: caller buffer (NW, reference layout)
     double *lam, *lamn, *s, *ds, *ym, *dym, *zL, *zU, *vL, *vU, *dw;
-    double *rec, *trec, *frec, *partt;
+    double *rec, *trec, *frec, *partt, *nuT, *nuTn;
     InstState* st;
 };
 struct OcpShared { const double *lbx, *ubx, *lbg, *ubg; IpmOpts o; };
@@ -110,6 +110,11 @@ struct OcpShared { const double *lbx, *ubx, *lbg, *ubg; IpmOpts o; };
 #define R_PART (R_GV + NGS)               // 10: cost, theta, dual_max, prim_max, ysum, zsum, nb, pmin, pmax, sum log(slack)
 #define NPART  10
 #define REC_SZ ((R_PART + NPART + 1) / 2 * 2)
+// terminal equality E x_N = x_s (TermCons, Control_Calc.py:197-198): NXT rows, multiplier nuT
+#ifndef MPCB_TERMCONS
+#define MPCB_TERMCONS 0
+#endif
+#define NXT (MPCB_TERMCONS ? NX : 0)
 // terminal record (x_N)
 #define T_H    0                          // NXA*NXA  Hessian of the terminal cost
 #define T_GN   (NXA * NXA)                  // NXA     its gradient
@@ -119,14 +124,17 @@ struct OcpShared { const double *lbx, *ubx, *lbg, *ubg; IpmOpts o; };
 #define T_ZU   (T_ZL + NXA)
 #define T_QL   (T_ZU + NXA)
 #define T_QU   (T_QL + NXA)
-#define T_PART (T_QU + NXA)                // 10: V, 0, dual_max, 0, 0, zsum, nb, pmin, pmax, sum log(slack)
+#define T_RT   (T_QU + NXA)                 // NXT     residual of the terminal equality
+#define T_PART (T_RT + NXT)                // 10: V, theta_T, dual_max, prim_T, |nuT|_1, zsum, nb, pmin, pmax, sum log(slack)
 #define TREC_SZ ((T_PART + NPART + 1) / 2 * 2)
 // forward records written by the Riccati sweep
 #define FREC_K   0
 #define FREC_KF  (NU * NXA)
-#define FREC_P   (FREC_KF + NU)
+#define FREC_GA  (FREC_KF + NU)            // NU*NXT   Gamma_k: du_k += Gamma_k nuT   (terminal equality)
+#define FREC_P   (FREC_GA + NU * NXT)
 #define FREC_PV  (FREC_P + NXA * NXA)
-#define FREC_SZ  ((FREC_PV + NXA + 1) / 2 * 2)
+#define FREC_PI  (FREC_PV + NXA)           // NXA*NXT  Pi_{k+1}: lam_k += Pi_{k+1} nuT
+#define FREC_SZ  ((FREC_PI + NXA * NXT + 1) / 2 * 2)
 
 struct OcpLayout {
     static constexpr int lam = 0;
@@ -145,7 +153,9 @@ struct OcpLayout {
     static constexpr int trec = rec + NH * REC_SZ;
     static constexpr int frec = trec + TREC_SZ;
     static constexpr int partt = frec + NH * FREC_SZ;
-    static constexpr int total = (partt + (NH + 1) * 4 + 1) / 2 * 2;
+    static constexpr int nuT = (partt + (NH + 1) * 4 + 1) / 2 * 2;      // multiplier of the terminal equality and its new value
+    static constexpr int nuTn = nuT + NXT;
+    static constexpr int total = (nuTn + NXT + 1) / 2 * 2;
 };
 
 MPCB_HD OcpInst ocp_inst(double* ws, double* wext, const double* par, InstState* st) {
@@ -155,7 +165,7 @@ MPCB_HD OcpInst ocp_inst(double* ws, double* wext, const double* par, InstState*
     I.ym = ws + OcpLayout::ym; I.dym = ws + OcpLayout::dym; I.vL = ws + OcpLayout::vL; I.vU = ws + OcpLayout::vU;
     I.zL = ws + OcpLayout::zL; I.zU = ws + OcpLayout::zU; I.dw = ws + OcpLayout::dw;
     I.rec = ws + OcpLayout::rec; I.trec = ws + OcpLayout::trec; I.frec = ws + OcpLayout::frec;
-    I.partt = ws + OcpLayout::partt;
+    I.partt = ws + OcpLayout::partt; I.nuT = ws + OcpLayout::nuT; I.nuTn = ws + OcpLayout::nuTn;
     return I;
 }
 
@@ -213,6 +223,7 @@ MPCB_HD void ocp_init_stage(OcpInst& I, const OcpShared& S, int k) {
         double chk = 0.0;
         for (int i = 0; i < MPCB_OFF_LAM; ++i) chk += I.par[i];
         if (!(chk == chk) || !fin(chk)) { st.state = ST_DONE; st.status = -13; }
+        for (int i = 0; i < NXT; ++i) I.nuT[i] = 0.0;
     }
     // state part z_k = [x_k; v_k]
     for (int i = 0; i < NXA; ++i) {
@@ -459,11 +470,23 @@ MPCB_HD void ocp_eval_stage(OcpInst& I, const OcpShared& S, int k) {
             bound_terms(w[wi], S.lbx[wi], S.ubx[wi], I.zL[wi], I.zU[wi], rf, true, &iL, &iU, &zL, &zU, &qL, &qU, &sig, &zs, &nbn, &pmn, &pmx, &prodN);
             const double gj = (j < NX) ? gN[j] : 0.0;
             t[T_IL + j] = iL; t[T_IU + j] = iU; t[T_ZL + j] = zL; t[T_ZU + j] = zU; t[T_QL + j] = qL; t[T_QU + j] = qU; t[T_GN + j] = gj;
-            dualN = fmax(dualN, fabs(gj - lam[j] + zU - zL));          // lam = lam_N for k = NH-1
+            double dr = gj - lam[j] + zU - zL;                           // lam = lam_N for k = NH-1
+#if MPCB_TERMCONS
+            if (j < NX) dr += I.nuT[j];
+#endif
+            dualN = fmax(dualN, fabs(dr));
 #pragma unroll
             for (int i = 0; i < NXA; ++i) t[T_H + i + NXA * j] = (i < NX && j < NX) ? HN[tri(i, j)] : 0.0;
         }
-        t[T_PART + 0] = V; t[T_PART + 1] = 0.0; t[T_PART + 2] = dualN; t[T_PART + 3] = 0.0; t[T_PART + 4] = 0.0;
+        double thT = 0.0, primT = 0.0, ysT = 0.0;
+#if MPCB_TERMCONS
+        {
+            double rT[NX];
+            ocp_termc(w + NH * NZA, I.par, rT);
+            for (int j = 0; j < NX; ++j) { t[T_RT + j] = rT[j]; thT += fabs(rT[j]); primT = fmax(primT, fabs(rT[j])); ysT += fabs(I.nuT[j]); }
+        }
+#endif
+        t[T_PART + 0] = V; t[T_PART + 1] = thT; t[T_PART + 2] = dualN; t[T_PART + 3] = primT; t[T_PART + 4] = ysT;
         t[T_PART + 5] = zs; t[T_PART + 6] = nbn; t[T_PART + 7] = pmn; t[T_PART + 8] = pmx; t[T_PART + 9] = log(prodN);
     }
 }
@@ -519,7 +542,15 @@ struct KktScratch {
     static constexpr int dx = F + (KKT_STAGED ? FREC_SZ : 0);   // NXA
     static constexpr int du = dx + NXA;                // NU
     static constexpr int dxn = du + NU;               // NXA
-    static constexpr int total = dxn + NXA;
+    // terminal equality: Pi (two buffers), B'Pi, Gamma, Gramian G, free response h, multiplier nu
+    static constexpr int PiA = dxn + NXA;             // NXA x NXT
+    static constexpr int PiB = PiA + NXA * NXT;
+    static constexpr int BtPi = PiB + NXA * NXT;      // NU x NXT
+    static constexpr int Ga = BtPi + NU * NXT;        // NU x NXT
+    static constexpr int Gm = Ga + NU * NXT;          // NXT x NXT
+    static constexpr int hT = Gm + NXT * NXT;         // NXT
+    static constexpr int nuS = hT + NXT;              // NXT
+    static constexpr int total = nuS + NXT;
 };
 
 // Streaming of the per-stage records by the sequential sweeps.  With 32 lanes the record of the NEXT stage to be
@@ -573,6 +604,19 @@ MPCB_HD bool ocp_riccati(OcpInst& I, double mu, double dwreg, double* sm) {
         }
         for (int i = lane; i < NXA; i += N_LANES) p[i] = t[T_GN + i] - mu * t[T_IL + i] + mu * t[T_IU + i];
     }
+#if MPCB_TERMCONS
+    // Terminal equality E dx_N = -r_T with multiplier nu (new value solved for directly).  By linearity of the sweep
+    // in the terminal gradient: p_k gains Pi_k nu, the feed-forward gains Gamma_k nu, and dx_N = h - G nu, with
+    //   Pi_N = E',  Pi_k = (A_k + B_k K_k)' Pi_{k+1},  Gamma_k = -Muu^{-1} B_k' Pi_{k+1},
+    //   G = sum_k (B_k' Pi_{k+1})' Muu^{-1} (B_k' Pi_{k+1}),   h = sum_k Pi_{k+1}' (B_k k_k + c_k)       (dx_0 = 0)
+    // all accumulated in this same backward sweep; the caller then solves G nu = h + r_T.
+    double* Pi = sm + KktScratch::PiA; double* Pn = sm + KktScratch::PiB;
+    double* BtPi = sm + KktScratch::BtPi; double* Ga = sm + KktScratch::Ga;
+    double* Gm = sm + KktScratch::Gm; double* hT = sm + KktScratch::hT;
+    for (int e = lane; e < NXA * NXT; e += N_LANES) Pi[e] = (e % NXA == e / NXA) ? 1.0 : 0.0;
+    for (int e = lane; e < NXT * NXT; e += N_LANES) Gm[e] = 0.0;
+    for (int e = lane; e < NXT; e += N_LANES) hT[e] = 0.0;
+#endif
     W_SYNC();
     RecStream rs;
     rec_prefetch(rs, I.rec + (NH - 1) * REC_SZ);
@@ -582,6 +626,15 @@ MPCB_HD bool ocp_riccati(OcpInst& I, double mu, double dwreg, double* sm) {
         // (a) P_{k+1}, p_{k+1} go to the forward record; slack coefficients
         for (int e = lane; e < NXA * NXA; e += N_LANES) fk[FREC_P + e] = P[e];
         for (int e = lane; e < NXA; e += N_LANES) fk[FREC_PV + e] = p[e];
+#if MPCB_TERMCONS
+        for (int e = lane; e < NXA * NXT; e += N_LANES) fk[FREC_PI + e] = Pi[e];
+        for (int e = lane; e < NU * NXT; e += N_LANES) {
+            const int l = e % NU, j = e / NU;
+            double a = 0.0;
+            for (int i = 0; i < NXA; ++i) a += R[R_AB + NXA * NXA + i + NXA * l] * Pi[i + NXA * j];
+            BtPi[e] = a;
+        }
+#endif
 #if NG > 0
         for (int r = lane; r < NG; r += N_LANES)
             cf[r] = (R[R_SG + r] + dwreg) * R[R_RG + r] - mu * R[R_ISL + r] + mu * R[R_ISU + r];
@@ -640,10 +693,14 @@ MPCB_HD bool ocp_riccati(OcpInst& I, double mu, double dwreg, double* sm) {
         }
         if (!pd) return false;                                   // uniform across the lanes
         // (e) K = -Muu^{-1} Mux (NU x NXA), kff = -Muu^{-1} q_u : one column per lane
-        for (int c = lane; c <= NXA; c += N_LANES) {
+        for (int c = lane; c <= NXA + NXT; c += N_LANES) {
             double y[NU];
             for (int i = 0; i < NU; ++i) {
+#if MPCB_TERMCONS
+                double a = (c < NXA) ? M[(NXA + i) + NZA * c] : ((c == NXA) ? q[NXA + i] : BtPi[i + NU * (c - NXA - 1)]);
+#else
                 double a = (c < NXA) ? M[(NXA + i) + NZA * c] : q[NXA + i];
+#endif
                 for (int l = 0; l < i; ++l) a -= L[i + NU * l] * y[l];
                 y[i] = a * Li[i];
             }
@@ -654,10 +711,38 @@ MPCB_HD bool ocp_riccati(OcpInst& I, double mu, double dwreg, double* sm) {
             }
             for (int i = 0; i < NU; ++i) {
                 if (c < NXA) { Kk[i + NU * c] = -y[i]; fk[FREC_K + i + NU * c] = -y[i]; }
-                else { kk[i] = -y[i]; fk[FREC_KF + i] = -y[i]; }
+                else if (c == NXA) { kk[i] = -y[i]; fk[FREC_KF + i] = -y[i]; }
+#if MPCB_TERMCONS
+                else { Ga[i + NU * (c - NXA - 1)] = -y[i]; fk[FREC_GA + i + NU * (c - NXA - 1)] = -y[i]; }
+#endif
             }
         }
         W_SYNC();
+#if MPCB_TERMCONS
+        for (int e = lane; e < NXA * NXT; e += N_LANES) {
+            const int i = e % NXA, j = e / NXA;
+            double a = 0.0;
+            for (int l = 0; l < NXA; ++l) a += R[R_AB + l + NXA * i] * Pi[l + NXA * j];
+            for (int m = 0; m < NU; ++m) a += Kk[m + NU * i] * BtPi[m + NU * j];
+            Pn[e] = a;
+        }
+        for (int e = lane; e < NXT * NXT; e += N_LANES) {
+            const int j1 = e % NXT, j2 = e / NXT;
+            double a = Gm[e];
+            for (int m = 0; m < NU; ++m) a -= BtPi[m + NU * j1] * Ga[m + NU * j2];
+            Gm[e] = a;
+        }
+        for (int j = lane; j < NXT; j += N_LANES) {
+            double a = hT[j];
+            for (int i = 0; i < NXA; ++i) {
+                double bc = R[R_C + i];
+                for (int m = 0; m < NU; ++m) bc += R[R_AB + NXA * NXA + i + NXA * m] * kk[m];
+                a += Pi[i + NXA * j] * bc;
+            }
+            hT[j] = a;
+        }
+        { double* tmp = Pi; Pi = Pn; Pn = tmp; }
+#endif
         // (f) P = Mxx + Mxu K (symmetrised), p = q_x + Mxu kff
         for (int e = lane; e < NXA * NXA; e += N_LANES) {
             const int i = e % NXA, j = e / NXA;
@@ -730,7 +815,7 @@ MPCB_HD void ocp_kkt(OcpInst& I, const OcpShared& S, double* sm) {
 #endif
     // ---- optimality error and termination (IPOPT: tol, dual_inf_tol=1, constr_viol_tol=1e-4, compl_inf_tol=1e-4)
     const double smax = 100.0;
-    const double mc = (double)(NH * NXA + NH * NG);
+    const double mc = (double)(NH * NXA + NH * NG + NXT);
     const double sd = fmax(smax, (ysum + zsum) / fmax(mc + nbd, 1.0)) / smax;
     const double sc = fmax(smax, zsum / fmax(nbd, 1.0)) / smax;
     const bool bounded = pmax >= pmin;
@@ -774,6 +859,45 @@ MPCB_HD void ocp_kkt(OcpInst& I, const OcpShared& S, double* sm) {
         if (dwreg > 1e40) break;
     }
     if (!ok) { ocp_finish(I, S, -3, fobj); return; }
+#if MPCB_TERMCONS
+    // ---- multiplier of the terminal equality: G nu = h + r_T (G is the horizon's reachability Gramian weighted by
+    //      Muu^{-1}: positive definite when x_s can be reached; otherwise IPOPT's jacobian_regularization delta_c)
+    {
+        const double* Gm = sm + KktScratch::Gm; const double* hT = sm + KktScratch::hT; double* nuS = sm + KktScratch::nuS;
+        double L[NXT * NXT + 1], y[NXT + 1];
+        bool pd = false;
+        for (int attempt = 0; attempt < 2 && !pd; ++attempt) {
+            const double dc = attempt ? 1e-8 * pow(mu, 0.25) : 0.0;
+            pd = true;
+            for (int j = 0; j < NXT; ++j) {
+                double djj = 0.5 * (Gm[j + NXT * j] + Gm[j + NXT * j]) + dc;
+                for (int l = 0; l < j; ++l) djj -= L[j + NXT * l] * L[j + NXT * l];
+                if (!(djj > 0.0)) { pd = false; break; }
+                djj = sqrt(djj);
+                L[j + NXT * j] = djj;
+                for (int i = j + 1; i < NXT; ++i) {
+                    double a = 0.5 * (Gm[i + NXT * j] + Gm[j + NXT * i]);
+                    for (int l = 0; l < j; ++l) a -= L[i + NXT * l] * L[j + NXT * l];
+                    L[i + NXT * j] = a / djj;
+                }
+            }
+        }
+        if (!pd) { ocp_finish(I, S, -3, fobj); return; }
+        for (int i = 0; i < NXT; ++i) {
+            double a = hT[i] + I.trec[T_RT + i];
+            for (int l = 0; l < i; ++l) a -= L[i + NXT * l] * y[l];
+            y[i] = a / L[i + NXT * i];
+        }
+        for (int i = NXT - 1; i >= 0; --i) {
+            double a = y[i];
+            for (int l = i + 1; l < NXT; ++l) a -= L[l + NXT * i] * y[l];
+            y[i] = a / L[i + NXT * i];
+        }
+        W_SYNC();
+        for (int i = lane; i < NXT; i += N_LANES) { nuS[i] = y[i]; I.nuTn[i] = y[i]; }
+        W_SYNC();
+    }
+#endif
     // ---- forward sweep, sequential part: only  du_k = K_k dx_k + k_k  and  dx_{k+1} = A dx_k + B du_k + c  (two lane
     //      phases per stage; the [A|B], c head of the record and the K, k head of the forward record are prefetched
     //      one stage ahead, one double per lane)
@@ -812,6 +936,9 @@ MPCB_HD void ocp_kkt(OcpInst& I, const OcpShared& S, double* sm) {
         for (int i = lane; i < NU; i += N_LANES) {
             double a = F[FREC_KF + i];
             for (int j = 0; j < NXA; ++j) a += F[FREC_K + i + NU * j] * dx[j];
+#if MPCB_TERMCONS
+            for (int j = 0; j < NXT; ++j) a += F[FREC_GA + i + NU * j] * sm[KktScratch::nuS + j];
+#endif
             du[i] = a;
             I.dw[k * NZA + NXA + i] = a;
         }
@@ -843,6 +970,9 @@ MPCB_HD void ocp_kkt(OcpInst& I, const OcpShared& S, double* sm) {
         for (int i = 0; i < NXA; ++i) {
             double a = F[FREC_PV + i];
             for (int j = 0; j < NXA; ++j) a += F[FREC_P + i + NXA * j] * dxn[j];
+#if MPCB_TERMCONS
+            for (int j = 0; j < NXT; ++j) a += F[FREC_PI + i + NXA * j] * sm[KktScratch::nuS + j];
+#endif
             I.lamn[k * NXA + i] = a;
         }
         for (int j = 0; j < NZA; ++j) {
@@ -954,7 +1084,15 @@ MPCB_HD void ocp_trial_stage(OcpInst& I, const OcpShared& S, int k) {
             if (fin(hi)) pN *= rhi(hi, rf) - xN[j];
         }
         ocp_term(xN, I.par, &V);
-        I.partt[NH * 4 + 0] = V; I.partt[NH * 4 + 1] = 0.0; I.partt[NH * 4 + 2] = log(pN);
+        double thT = 0.0;
+#if MPCB_TERMCONS
+        {
+            double rT[NX];
+            ocp_termc(xN, I.par, rT);
+            for (int j = 0; j < NX; ++j) thT += fabs(rT[j]);
+        }
+#endif
+        I.partt[NH * 4 + 0] = V; I.partt[NH * 4 + 1] = thT; I.partt[NH * 4 + 2] = log(pN);
     }
 }
 
@@ -1047,6 +1185,7 @@ MPCB_HD void ocp_accept(OcpInst& I, const OcpShared& S) {
         I.w[i] = wn;
     }
     for (int i = lane; i < NH * NXA; i += N_LANES) I.lam[i] += alpha * (I.lamn[i] - I.lam[i]);
+    for (int i = lane; i < NXT; i += N_LANES) I.nuT[i] += alpha * (I.nuTn[i] - I.nuT[i]);
 #if NG > 0
     for (int i = lane; i < NH * NG; i += N_LANES) {
         const double lo = S.lbg[i], hi = S.ubg[i], dv = I.ds[i];

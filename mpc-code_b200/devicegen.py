@@ -161,8 +161,11 @@ def generate_header(prob, ss_spec, ocp_spec, opts: Optional[Dict] = None) -> Dic
         o = ocp_spec
         if o.flags["ContForm"] is True and o.uses_uprev:
             raise NotImplementedError("ContForm together with Delta-u terms is not on the device path")
-        if o.term_eq is not None:
-            raise NotImplementedError("TermCons (terminal equality) is not on the device path yet")
+        if o.term_eq is not None:                       # TermCons: X_N - x_s = 0 (X_N = 0 without QForm), Control_Calc.py:194-198
+            Jt = jacobian(o.term_eq, o.XN)
+            ident = all((e.op == "const" and float(e.val) == (1.0 if i % (o.n + 1) == 0 else 0.0)) for i, e in enumerate(Jt.elements()))
+            if not ident:
+                raise NotImplementedError("terminal equality must have the form X_N - const")
         # Delta-u costs / bounds couple u_k with u_{k-1} (Control_Calc.py:163-169,180-183): the device carries
         # u_{k-1} as extra state components v_k (z_k = [x_k; v_k], v_{k+1} = u_k), so every stage map stays local.
         naug = m_ = o.m if o.uses_uprev else 0
@@ -205,6 +208,9 @@ def generate_header(prob, ss_spec, ocp_spec, opts: Optional[Dict] = None) -> Dic
         Hc, gc = hessian(stage_cost, zz)
         fns.append(CFunction("ocp_cost", ins_c, [("l", stage_cost)]))
         fns.append(CFunction("ocp_cost_d", ins_c, [("l", stage_cost), ("g", gc), ("H", tril_pack(Hc))]))
+        D["MPCB_TERMCONS"] = int(o.term_eq is not None)
+        if o.term_eq is not None:
+            fns.append(CFunction("ocp_termc", [("XN", o.XN), ("par", par)], [("r", o.term_eq)]))
         Ht, gt = hessian(o.term_cost, o.XN)
         fns.append(CFunction("ocp_term", [("XN", o.XN), ("par", par)], [("V", o.term_cost)]))
         fns.append(CFunction("ocp_term_d", [("XN", o.XN), ("par", par)],

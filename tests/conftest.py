@@ -87,7 +87,7 @@ class Bundle:
     def ocp_range_bounds(self):
         """Range rows of g_lb/g_ub stage by stage: [Y_k bounds, DU_k bounds] for k = 0..N-1 (see include/mpcb.h)."""
         o = self.ocp
-        n_dyn = o.n * (o.N + 1)
+        n_dyn = o.n * (o.N + 1) + (o.n if o.term_eq is not None else 0)
         ny_rows = 0 if o.yFree else o.p * o.N
         ndu_rows = 0 if o.DuFree else o.m * o.N
 
