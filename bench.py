@@ -345,10 +345,10 @@ def run_gpu(args):
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         pool = OraclePool(cores)
-        v, wall = pool.throughput(cores, 10)
+        v, wall = pool.throughput(cores, 60)
         pool.close()
         cpu_baseline = {"value": v, "unit": "steps/s", "cores": cores, "kind": "port",
-                        "sample": "%d instances x 10 closed-loop steps of the same workload, one process per core (%.1f s); "
+                        "sample": "%d instances x 60 closed-loop steps of the same workload, one process per core (%.1f s); "
                                   "dense-KKT oracle port, not IPOPT" % (cores, wall)}
     clocks = _parse_clocks(clock_file, local, windows)
     out = {

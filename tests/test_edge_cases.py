@@ -1,0 +1,85 @@
+"""Edge cases of the OCP solve, device code (CPU harness build) against the oracle with the SAME options:
+iteration limit, option variants (bound handling, barrier start, tolerance), a start on the bounds, identical
+instances in a ragged batch."""
+import numpy as np
+import pytest
+
+from oracle.ipm import IpmOptions
+from oracle.nlp import OcpNlp
+
+
+def _case(nmpc, scale=0.01, seed=0):
+    p = nmpc.prob
+    rng = np.random.default_rng(seed)
+    xh = p.x0_m * (1 + scale * np.array([1.0, 0.1, 1.0]) * rng.uniform(-1, 1, p.nx))
+    par = nmpc.ocp_par(xh, p.x0_m, p.u0, p.dhat0)
+    lb, ub = nmpc.ocp.w_lb.copy(), nmpc.ocp.w_ub.copy(); lb[:p.nx] = ub[:p.nx] = xh
+    return par, lb, ub
+
+
+def test_iteration_limit_reports_maximum_iterations_exceeded(nmpc):
+    par, lb, ub = _case(nmpc)
+    w, f, st, it, _ = nmpc.harness_ocp(par, nmpc.cold_guess(), max_iter=3)
+    r = OcpNlp(nmpc.ocp, nmpc.oracle).solve(nmpc.cold_guess(), par, lb, ub, opts=IpmOptions(max_iter=3))
+    assert st[0] == -1 and r.status == -1 and it[0] == r.iters == 3
+    assert np.abs(w[0] - r.x).max() < 1e-9                  # the same (unfinished) iterate
+
+
+@pytest.mark.parametrize("kw,okw", [
+    (dict(honor=1), dict(honor_original_bounds=True)),
+    (dict(mu_init=1e-2), dict(mu_init=1e-2)),
+    (dict(tol=1e-6), dict(tol=1e-6)),
+    (dict(relax=0.0), dict(bound_relax_factor=0.0)),
+])
+def test_option_variants_follow_the_oracle(nmpc, kw, okw):
+    par, lb, ub = _case(nmpc, seed=3)
+    w, f, st, it, _ = nmpc.harness_ocp(par, nmpc.cold_guess(), **kw)
+    r = OcpNlp(nmpc.ocp, nmpc.oracle).solve(nmpc.cold_guess(), par, lb, ub, opts=IpmOptions(max_iter=100, **okw))
+    assert st[0] == r.status == 0 and it[0] == r.iters
+    assert np.abs(w[0] - r.x).max() < 1e-6 and abs(f[0] - r.f) <= 1e-8 * max(1.0, abs(r.f))
+    if "honor" in kw:                                       # IPOPT 3.12 behaviour: the solution is clipped into the original bounds
+        assert np.all(w[0] >= lb - 1e-15) and np.all(w[0] <= ub + 1e-15)
+
+
+def test_guess_on_the_bounds_is_pushed_inside(nmpc):
+    """IPOPT's bound_push: a warm start sitting exactly on umin / xmax must give the same solve as the oracle's."""
+    p = nmpc.prob
+    par, lb, ub = _case(nmpc, seed=5)
+    g = nmpc.cold_guess().copy()
+    nz = p.nx + p.nu
+    for k in range(p.N):
+        g[k * nz + p.nx] = nmpc.ocp.bounds["umin"][0]       # every u_k[0] on its lower bound
+        g[(k + 1) * nz + 2] = nmpc.ocp.bounds["xmax"][2]    # every level on its upper bound
+    w, f, st, it, _ = nmpc.harness_ocp(par, g)
+    r = OcpNlp(nmpc.ocp, nmpc.oracle).solve(g, par, lb, ub, opts=IpmOptions(max_iter=100))
+    assert st[0] == r.status == 0 and it[0] == r.iters and np.abs(w[0] - r.x).max() < 1e-6
+
+
+def test_ragged_batch_of_identical_and_distinct_instances(nmpc):
+    """37 instances (not a multiple of any block size): identical inputs give bit-identical outputs wherever they sit
+    in the batch, and a distinct one in the middle does not disturb its neighbours."""
+    par, _, _ = _case(nmpc, seed=7)
+    other, _, _ = _case(nmpc, scale=0.02, seed=8)
+    P = np.tile(par, (37, 1)); P[17] = other
+    w, f, st, it, _ = nmpc.harness_ocp(P, np.tile(nmpc.cold_guess(), (37, 1)))
+    same = [i for i in range(37) if i != 17]
+    assert np.all(st == 0)
+    assert np.all(w[same] == w[0]) and np.all(f[same] == f[0]) and np.all(it[same] == it[0])
+    w1, f1, _, _, _ = nmpc.harness_ocp(other, nmpc.cold_guess())
+    assert np.array_equal(w[17], w1[0]) and f[17] == f1[0]
+
+
+@pytest.mark.gpu
+def test_gpu_single_instance_and_iteration_limit(nmpc):
+    from mpc_code_b200.mpc_loop import CompiledProblem
+    from mpc_code_b200.solvers import MpcbHandle, BatchedNlpSolver
+    cp = CompiledProblem(nmpc.prob, "nmpc_cstr")
+    par, lb, ub = _case(nmpc)
+    on = OcpNlp(nmpc.ocp, nmpc.oracle)
+    for max_iter, status in ((100, 0), (3, -1)):
+        h = MpcbHandle(cp.library, 1, dict(max_iter=100), dict(max_iter=max_iter))
+        solver = BatchedNlpSolver("ocp", cp.ocp_spec).attach(h)
+        sol = solver(x0=nmpc.cold_guess()[None, :], p=par[None, :])
+        r = on.solve(nmpc.cold_guess(), par, lb, ub, opts=IpmOptions(max_iter=max_iter))
+        assert int(solver.stats()["status"][0]) == status == r.status
+        assert np.abs(sol["x"].cpu().numpy()[0] - r.x).max() < 1e-6
