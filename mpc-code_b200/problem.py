@@ -219,8 +219,20 @@ def build_problem(ns: Dict[str, Any]) -> MpcProblem:
         raise SystemExit("The disturbance dimension is not zero but no disturbance model has been selected")
     est: Dict[str, Any] = {}
     if ns["kalss"] is True or ns["lue"] is True:
-        if ns["kalss"] is True and "K" not in ns:
-            raise NotImplementedError("kalss=True needs the steady-state gain K (Kkalss is host-side setup, out of scope)")
+        if ns["kalss"] is True:                                     # steady-state gain (MPC_code.py:339-363)
+            from .estimator_setup import Kkalss
+            have_A, have_C = "A" in ns, "C" in ns
+            linmod = "full" if (have_A and have_C) else ("onlyA" if have_A else ("onlyC" if have_C else "no"))
+            kwk = {}
+            if offree == "lin": kwk.update(Bd=ns["Bd"], Cd=ns["Cd"])
+            if have_A: kwk["A"] = ns["A"]
+            else: kwk["Fx"] = Fx_model
+            if have_C: kwk["C"] = ns["C"]
+            else: kwk["Fy"] = Fy_model
+            var = () if linmod == "full" else (x, u, k, d, t, h, px, py, ns.get("x_ss"), ns.get("u_ss"), ns.get("px_ss"), ns.get("py_ss"))
+            if linmod != "full" and ("x_ss" not in ns or "u_ss" not in ns):
+                raise SystemExit("kalss with a nonlinear model needs the linearisation point x_ss, u_ss")
+            ns["K"] = Kkalss(ny, nd, nx, ns["Q_kf"], ns["R_kf"], offree, linmod, *var, **kwk)
         K = np.eye(nxi) if (SF is True and offree == "no") else np.asarray(ns["K"], dtype=float)
         est = dict(type="kalss", K=K.reshape(nxi, ny))
     elif ns["mhe"] is True:
