@@ -92,20 +92,18 @@ struct OcpShared { const double *lbx, *ubx, *lbg, *ubg; IpmOpts o; };
 #define R_GL   (R_M + NZA * NZA)            // NZA     gradient of the stage cost
 #define R_IL   (R_GL + NZA)                // NZA     1 / (v - lo)  (0: no lower bound / fixed x_0)
 #define R_IU   (R_IL + NZA)                // NZA     1 / (hi - v)
-#define R_ZL   (R_IU + NZA)                // NZA
-#define R_ZU   (R_ZL + NZA)                // NZA
-#define R_QL   (R_ZU + NZA)                // NZA     (1/(v-lo)) / zL   (0: no bound) - keeps the step-size rules division free
-#define R_QU   (R_QL + NZA)                // NZA     (1/(hi-v)) / zU
-#define R_G    (R_QU + NZA)                // NG*NZA  Jacobian of the range rows (column-major NG x NZA)
+#define R_G    (R_IU + NZA)                // NG*NZA  Jacobian of the range rows (column-major NG x NZA)
 #define R_SG   (R_G + NGS * NZA)           // NG     Sigma_s = vL/(s-lo) + vU/(hi-s)
 #define R_ISL  (R_SG + NGS)               // NG     1 / (s - lo)
 #define R_ISU  (R_ISL + NGS)              // NG     1 / (hi - s)
-#define R_VL   (R_ISU + NGS)              // NG
-#define R_VU   (R_VL + NGS)               // NG
-#define R_QSL  (R_VU + NGS)               // NG     (1/(s-lo)) / vL
+#define R_RG   (R_ISU + NGS)              // NG     g - s
+#define R_BWD  (R_RG + NGS)               // ---- everything above is what the backward sweep stages (one burst);
+                                          //      the stage-parallel pass reads R_GL .. R_GV (one burst); order matters
+#define R_QL   R_BWD                      // NZA     (1/(v-lo)) / zL   (0: no bound) - keeps the step-size rules division free
+#define R_QU   (R_QL + NZA)                // NZA     (1/(hi-v)) / zU
+#define R_QSL  (R_QU + NZA)                // NG     (1/(s-lo)) / vL
 #define R_QSU  (R_QSL + NGS)              // NG     (1/(hi-s)) / vU
-#define R_RG   (R_QSU + NGS)              // NG     g - s
-#define R_YM   (R_RG + NGS)               // NG     multiplier of the range row
+#define R_YM   (R_QSU + NGS)              // NG     multiplier of the range row
 #define R_GV   (R_YM + NGS)               // NG     g
 #define R_PART (R_GV + NGS)               // 10: cost, theta, dual_max, prim_max, ysum, zsum, nb, pmin, pmax, sum log(slack)
 #define NPART  10
@@ -389,7 +387,7 @@ MPCB_HD void ocp_eval_stage(OcpInst& I, const OcpShared& S, int k) {
         const bool active = !(k == 0 && j < NXA);          // x_0 is fixed
         double iL, iU, zL, zU, qL, qU;
         bound_terms(w[wi], S.lbx[wi], S.ubx[wi], I.zL[wi], I.zU[wi], rf, active, &iL, &iU, &zL, &zU, &qL, &qU, &dg[j], &zsum, &nb, &pmin, &pmax, &prod);
-        r[R_IL + j] = iL; r[R_IU + j] = iU; r[R_ZL + j] = zL; r[R_ZU + j] = zU; r[R_QL + j] = qL; r[R_QU + j] = qU; r[R_GL + j] = g[j];
+        r[R_IL + j] = iL; r[R_IU + j] = iU; r[R_QL + j] = qL; r[R_QU + j] = qU; r[R_GL + j] = g[j];
         res[j] += zU - zL;
     }
     double M[NZA * NZA], dual_s = 0.0;
@@ -416,7 +414,7 @@ MPCB_HD void ocp_eval_stage(OcpInst& I, const OcpShared& S, int k) {
             double isl, isu, vl, vu, qsl, qsu, sig = 0.0;
             bound_terms(sv, lo, hi, I.vL[gi], I.vU[gi], rf, true, &isl, &isu, &vl, &vu, &qsl, &qsu, &sig, &zsum, &nb, &pmin, &pmax, &prod);
             const double rg = Y[q] - sv;
-            r[R_SG + q] = sig; r[R_ISL + q] = isl; r[R_ISU + q] = isu; r[R_VL + q] = vl; r[R_VU + q] = vu;
+            r[R_SG + q] = sig; r[R_ISL + q] = isl; r[R_ISU + q] = isu;
             r[R_QSL + q] = qsl; r[R_QSU + q] = qsu;
             r[R_RG + q] = rg; r[R_YM + q] = mult[q]; r[R_GV + q] = Y[q];
             th += fabs(rg); prim = fmax(prim, fabs(rg)); ysum += fabs(mult[q]);
@@ -529,7 +527,7 @@ MPCB_HD void ocp_eval_stage(OcpInst& I, const OcpShared& S, int k) {
 // scratch (doubles): shared memory per warp with 32 lanes, thread-local (registers) with one lane
 struct KktScratch {
     static constexpr int R = 0;                                     // staged record (32-lane mapping only)
-    static constexpr int P = R + (KKT_STAGED ? REC_SZ : 0);   // NXA x NXA  cost-to-go Hessian of the next stage
+    static constexpr int P = R + (KKT_STAGED ? (R_BWD + 1) / 2 * 2 : 0);   // NXA x NXA  cost-to-go Hessian of the next stage
     static constexpr int p = P + NXA * NXA;             // NXA
     static constexpr int M = p + NXA;                  // NZA x NZA  condensed stage Hessian
     static constexpr int q = M + NZA * NZA;             // NZA
@@ -558,14 +556,14 @@ struct KktScratch {
 // only copied to shared memory when its turn comes: the DRAM/L2 latency of the load overlaps the arithmetic
 // (ncu before this: 54 % of the kernel's stall samples sat on the record copy).  With one lane the record is read in
 // place.
-#define REC_PER_LANE ((R_PART + MPCB_KKT_LANES - 1) / MPCB_KKT_LANES)
+#define REC_PER_LANE ((R_BWD + MPCB_KKT_LANES - 1) / MPCB_KKT_LANES)
 struct RecStream {
     double pre[REC_PER_LANE];
 };
 MPCB_HD void rec_prefetch(RecStream& rs, const double* rk) {
 #if KKT_ON_LANES
 #pragma unroll
-    for (int q = 0; q < REC_PER_LANE; ++q) { const int e = LANE_ID + N_LANES * q; rs.pre[q] = (e < R_PART) ? rk[e] : 0.0; }
+    for (int q = 0; q < REC_PER_LANE; ++q) { const int e = LANE_ID + N_LANES * q; rs.pre[q] = (e < R_BWD) ? rk[e] : 0.0; }
 #else
     (void)rs; (void)rk;
 #endif
@@ -576,7 +574,7 @@ MPCB_HD const double* stage_record(RecStream& rs, const double* rk, const double
     double* R = sm + KktScratch::R;
     W_SYNC();
 #pragma unroll
-    for (int q = 0; q < REC_PER_LANE; ++q) { const int e = LANE_ID + N_LANES * q; if (e < R_PART) R[e] = rs.pre[q]; }
+    for (int q = 0; q < REC_PER_LANE; ++q) { const int e = LANE_ID + N_LANES * q; if (e < R_BWD) R[e] = rs.pre[q]; }
     if (rk_next) rec_prefetch(rs, rk_next);
     W_SYNC();
     return R;
