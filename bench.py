@@ -338,6 +338,7 @@ def run_gpu(args):
         "hbm": {"achieved": ach_gb, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gb / hbm_peak, "bytes_per_stage_eval": b_stage,
                 "peak_source": hbm_src},
         "kernel_time_share": {c: kms[c] / max(sum(kms.values()), 1e-12) for c in kms}, "dominant_by_time": dom,
+        "line_search_trials_per_iteration": prof["trial_instances"] / max(prof["eval_instances"], 1),
     }
 
     # ---------------- CPU baseline beside it (bounded sample) ----------------
