@@ -72,8 +72,8 @@ const char* mpcb_last_error(mpcb_handle_t h);
  *   "ocp_lbx","ocp_ubx" [nw]  - w_lb / w_ub of opt_dyn (Control_Calc.py:213-252); entries 0..nx-1
  *                               are ignored, x0 is fixed from par[0:nx] (MPC_code.py:734)
  *   "ocp_lbg","ocp_ubg" [ng*N]- the range rows of g_lb / g_ub, stage by stage: for k = 0..N-1 the ny bounds of
- *                               Y_k (Control_Calc.py:227-230) followed by the nu bounds of DU_k (:241-243); ng counts
- *                               the blocks that are present
+ *                               Y_k (Control_Calc.py:227-230), the nu bounds of DU_k (:241-243) and the bounds
+ *                               (-inf, 0) of the user inequalities G_k (:244-245); ng counts the blocks that are present
  *   "ss_lbx","ss_ubx"   [nwss]- wss_lb / wss_ub of opt_ss (Target_Calc.py:127-134)
  *   "Q_kf" [nxi*nxi], "R_kf" [ny*ny], "K_est" [nxi*ny] (row-major), "dmin","dmax" [nd]
  */

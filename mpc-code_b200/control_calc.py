@@ -36,6 +36,7 @@ class OcpSpec:
     w_lb: np.ndarray; w_ub: np.ndarray; g_lb: np.ndarray; g_ub: np.ndarray
     bounds: Dict[str, np.ndarray]
     sol_opts: Dict[str, Any] = field(default_factory=dict)
+    G: Optional[SX] = None              # user stage inequalities G_ineq(X,U,Y,d,t,pxk,pyk) <= 0   (:94-96,132-137,244-245)
     quad_cost: Optional[SX] = None      # ContForm: integrand of the stage cost     (:102-111)
     cont_rhs: Optional[SX] = None       # ContForm: ode right-hand side fx(...)+px  (:103)
     cont_substeps: int = 0
@@ -46,6 +47,10 @@ class OcpSpec:
         ids = {e.uid for e in self.Uprev.elements()}
         exprs = list(self.stage_cost.elements())
         return (not self.DuFree) or any(s.uid in ids for s in S.symbols_of(exprs))
+
+    @property
+    def n_gin(self) -> int:
+        return 0 if self.G is None else self.G.numel()
 
     @property
     def ng(self) -> int:
@@ -71,8 +76,8 @@ def build_ocp_spec(xSX, uSX, ySX, dSX, tSX, pxSX, pySX, n, m, p, nd, npx, npy, n
                    sol_opts, G_ineq, H_eq, umin=None, umax=None, W=None, Z=None, ymin=None, ymax=None,
                    xmin=None, xmax=None, Dumin=None, Dumax=None, h=None, fx=None, xstat=None, ustat=None,
                    Ws=None) -> OcpSpec:
-    if slacks is True or G_ineq is not None or H_eq is not None:
-        raise NotImplementedError("slack variables and user g/h constraints are outside the accelerated path")
+    if slacks is True or H_eq is not None:
+        raise NotImplementedError("slack variables and user equality constraints h are outside the accelerated path")
     nxu = n + m
     if nw != nxu * N + n:
         raise ValueError("nw must be n*(N+1)+m*N without slacks (Control_Calc.py:28)")
@@ -99,6 +104,11 @@ def build_ocp_spec(xSX, uSX, ySX, dSX, tSX, pxSX, pySX, n, m, p, nd, npx, npy, n
     ys = Fy_model(xs, us, d, t, py0)                                # (:124)
     Y = Fy_model(X, U, d, t, pyk) + mtimes(lam, U - us)            # (:130)
     DU = U - Uprev                                                  # (:163-166)
+    G = None
+    if G_ineq is not None:                                          # (:94-96,132-137): evaluated with the corrected Y_k
+        G = SX(G_ineq(X, U, Y, d, t, pxk, pyk))
+        if G.numel() == 0:
+            G = None
     quad_cost = cont_rhs = None
     if ContForm is True:                                            # (:102-111,153-158)
         # The reference integrates  xdot = fx(x,u,d,t,px) + px  together with the quadrature of the stage cost over
@@ -138,11 +148,14 @@ def build_ocp_spec(xSX, uSX, ySX, dSX, tSX, pxSX, pySX, n, m, p, nd, npx, npy, n
     ng = n * (N + 1) + (n if TermCons is True else 0)
     ng1 = 0 if yFree else p * N
     ng2 = 0 if DuFree else m * N
-    g_lb = np.zeros(ng + ng1 + ng2); g_ub = np.zeros(ng + ng1 + ng2)
+    ng4 = 0 if G is None else G.numel() * N
+    g_lb = np.zeros(ng + ng1 + ng2 + ng4); g_ub = np.zeros(ng + ng1 + ng2 + ng4)
     if ng1:
         g_lb[ng:ng + ng1] = np.tile(ymin_v, N); g_ub[ng:ng + ng1] = np.tile(ymax_v, N)
     if ng2:
-        g_lb[ng + ng1:] = np.tile(Dumin_v, N); g_ub[ng + ng1:] = np.tile(Dumax_v, N)
+        g_lb[ng + ng1:ng + ng1 + ng2] = np.tile(Dumin_v, N); g_ub[ng + ng1:ng + ng1 + ng2] = np.tile(Dumax_v, N)
+    if ng4:
+        g_lb[ng + ng1 + ng2:] = -np.inf                             # (:244-245)
 
     flags = dict(QForm=QForm, DUForm=DUForm, DUFormEcon=DUFormEcon, ContForm=ContForm, TermCons=TermCons)
     return OcpSpec(n=n, m=m, p=p, nd=nd, npx=npx, npy=npy, N=N, h=float(h), nw=nw, npar=off["end"], off=off,
@@ -152,7 +165,7 @@ def build_ocp_spec(xSX, uSX, ySX, dSX, tSX, pxSX, pySX, n, m, p, nd, npx, npy, n
                    w_lb=w_lb, w_ub=w_ub, g_lb=g_lb, g_ub=g_ub,
                    bounds=dict(xmin=xmin_v, xmax=xmax_v, umin=umin_v, umax=umax_v, ymin=ymin_v, ymax=ymax_v,
                                Dumin=Dumin_v, Dumax=Dumax_v),
-                   sol_opts=dict(sol_opts or {}), quad_cost=quad_cost, cont_rhs=cont_rhs,
+                   sol_opts=dict(sol_opts or {}), G=G, quad_cost=quad_cost, cont_rhs=cont_rhs,
                    cont_substeps=(int(Fx_model.meta.get("substeps", 10)) if ContForm is True else 0))
 
 

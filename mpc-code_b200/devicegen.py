@@ -169,9 +169,9 @@ def generate_header(prob, ss_spec, ocp_spec, opts: Optional[Dict] = None) -> Dic
         # Delta-u costs / bounds couple u_k with u_{k-1} (Control_Calc.py:163-169,180-183): the device carries
         # u_{k-1} as extra state components v_k (z_k = [x_k; v_k], v_{k+1} = u_k), so every stage map stays local.
         naug = m_ = o.m if o.uses_uprev else 0
-        n_rows = (0 if o.yFree else o.p) + (0 if o.DuFree else o.m)
+        n_rows = (0 if o.yFree else o.p) + (0 if o.DuFree else o.m) + o.n_gin
         D.update(MPCB_HAS_OCP=1, MPCB_NW=o.nw, MPCB_NPAR=o.npar, MPCB_NG=n_rows, MPCB_NAUG=naug,
-                 MPCB_NGY=(0 if o.yFree else o.p), MPCB_NGDU=(0 if o.DuFree else o.m))
+                 MPCB_NGY=(0 if o.yFree else o.p), MPCB_NGDU=(0 if o.DuFree else o.m), MPCB_NGIN=o.n_gin)
         for k_, v_ in o.off.items():
             D["MPCB_OFF_%s" % k_.upper()] = v_
         X, U, Up, par, pxk, pyk = o.X, o.U, o.Uprev, o.par, o.pxk, o.pyk
@@ -221,6 +221,10 @@ def generate_header(prob, ss_spec, ocp_spec, opts: Optional[Dict] = None) -> Dic
                 rows.append(o.Y)
             if not o.DuFree:
                 rows.append(o.DU)
+            if o.G is not None:                         # user stage inequalities, after the Y and DU rows
+                if _depends_on(o.G, pxk):
+                    raise NotImplementedError("User_g_ineq depending on the state-map parameters px is not on the device path")
+                rows.append(o.G)
             R = vertcat(*rows)
             mult = SX.sym("mult", n_rows)
             Hy, _ = hessian(mtimes(mult.T, R), zz)

@@ -282,10 +282,13 @@ def make_specs(prob: MpcProblem):
     if "User_fobj_Cont" in prob.ns:
         extra = dict(fx=prob.ns["User_fxm_Cont"], xstat=s["xs"], ustat=s["us"])
     f = prob.flags
+    for name in ("User_h_eq", "User_g_ineq_SS", "User_h_eq_SS"):
+        if prob.ns.get(name) is not None:
+            raise NotImplementedError("%s is outside the accelerated path (stage inequalities User_g_ineq are supported)" % name)
     ocp = build_ocp_spec(s["x"], s["u"], s["y"], s["d"], s["t"], s["px"], s["py"], prob.nx, prob.nu, prob.ny, prob.nd,
                          prob.npx, prob.npy, 0, 0, prob.Fx_model, prob.Fy_model, prob.F_obj, prob.Vfin, prob.N,
                          f["QForm"], f["DUForm"], f["DUFormEcon"], f["ContForm"], f["TermCons"], False, True, True,
-                         prob.nw, prob.sol_optdyn, None, None, umin=b["umin"], umax=b["umax"], W=None, Z=None,
+                         prob.nw, prob.sol_optdyn, prob.ns.get("User_g_ineq"), None, umin=b["umin"], umax=b["umax"], W=None, Z=None,
                          ymin=b["ymin"], ymax=b["ymax"], xmin=b["xmin"], xmax=b["xmax"], Dumin=b["Dumin"],
                          Dumax=b["Dumax"], h=prob.h, Ws=[], **extra)
     return ss, ocp

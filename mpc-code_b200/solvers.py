@@ -341,12 +341,16 @@ class BatchedNlpSolver:
             # g = [dynamics | Y_k rows (all k) | DU_k rows (all k)]  (Control_Calc.py:200-204,254) -> stage-interleaved
             ny_rows = 0 if s.yFree else s.p * s.N
             ndu_rows = 0 if s.DuFree else s.m * s.N
+            ngin_rows = s.n_gin * s.N
             def per_stage(v):
                 blocks = []
                 if ny_rows:
                     blocks.append(v[n_dyn:n_dyn + ny_rows].reshape(s.N, s.p))
                 if ndu_rows:
                     blocks.append(v[n_dyn + ny_rows:n_dyn + ny_rows + ndu_rows].reshape(s.N, s.m))
+                if ngin_rows:
+                    o3 = n_dyn + ny_rows + ndu_rows
+                    blocks.append(v[o3:o3 + ngin_rows].reshape(s.N, s.n_gin))
                 return np.hstack(blocks).reshape(-1) if blocks else np.zeros(0)
             h.set_const("ocp_lbg", per_stage(lbg)); h.set_const("ocp_ubg", per_stage(ubg))
         else:

@@ -43,6 +43,13 @@ def ocp_functions(spec):
     Hy, _ = _scalar_hess(mtimes(mult[0:p].T, spec.Y) if p else SX(0.0), z)
     fns.append(CFunction("orc_out_d", ins_y + [("mult", mult)],
                          [("Y", spec.Y), ("JY", jacobian(spec.Y, z)), ("HY", Hy)]))
+    if getattr(spec, "G", None) is not None:        # user stage inequalities (Control_Calc.py:132-137)
+        ng_in = spec.G.numel()
+        multg = SX.sym("multg", ng_in)
+        ins_g = [("X", X), ("U", U), ("par", par), ("pxk", pxk), ("pyk", pyk)]
+        Hg, _ = _scalar_hess(mtimes(multg.T, spec.G), z)
+        fns.append(CFunction("orc_gin", ins_g, [("G", spec.G)]))
+        fns.append(CFunction("orc_gin_d", ins_g + [("multg", multg)], [("G", spec.G), ("JG", jacobian(spec.G, z)), ("HG", Hg)]))
     zc = vertcat(X, U, Up)
     ins_c = [("X", X), ("U", U), ("Up", Up), ("par", par), ("pxk", pxk), ("pyk", pyk)]
     Hc, gc = _scalar_hess(spec.stage_cost, zc)

@@ -20,7 +20,8 @@ class OcpNlp:
         self.n_dyn = s.n * (s.N + 1) + (s.n if s.term_eq is not None else 0)
         self.n_y = 0 if s.yFree else s.p * s.N
         self.n_du = 0 if s.DuFree else s.m * s.N
-        self.m_total = self.n_dyn + self.n_y + self.n_du
+        self.n_gin = getattr(s, "n_gin", 0)                  # user stage inequalities, rows after the DU rows (Control_Calc.py:254)
+        self.m_total = self.n_dyn + self.n_y + self.n_du + self.n_gin * s.N
         assert self.m_total == s.g_lb.size
 
     def _slices(self, par, k):
@@ -37,6 +38,7 @@ class OcpNlp:
         xs = par[s.off["xs"]:s.off["xs"] + n]
         um1 = par[s.off["um1"]:s.off["um1"] + m]
         oy, odu = self.n_dyn, self.n_dyn + self.n_y
+        ogi, ngi = self.n_dyn + self.n_y + self.n_du, self.n_gin
 
         def fun(w, lam, need):
             g = np.zeros(self.m_total)
@@ -78,6 +80,15 @@ class OcpNlp:
                         J[dr, nxu * k + n:nxu * (k + 1)] = np.eye(m)
                         if k > 0:
                             J[dr, nxu * (k - 1) + n:nxu * k] = -np.eye(m)
+                if ngi:
+                    gr = slice(ogi + ngi * k, ogi + ngi * (k + 1))
+                    if need >= 2:
+                        Gv, JG, HG = c.orc_gin_d(X, U, par, pxk, pyk, lam[gr])
+                        J[gr, iz] = JG
+                        H[iz, iz] += HG
+                    else:
+                        Gv = c.orc_gin(X, U, par, pxk, pyk)
+                    g[gr] = np.asarray(Gv).ravel()
                 if need >= 1:
                     l, gc, Hc = c.orc_cost_d(X, U, Up, par, pxk, pyk)
                     f += float(l[0, 0])

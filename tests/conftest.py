@@ -90,6 +90,7 @@ class Bundle:
         n_dyn = o.n * (o.N + 1) + (o.n if o.term_eq is not None else 0)
         ny_rows = 0 if o.yFree else o.p * o.N
         ndu_rows = 0 if o.DuFree else o.m * o.N
+        ngin_rows = o.n_gin * o.N
 
         def per_stage(v):
             blocks = []
@@ -97,6 +98,9 @@ class Bundle:
                 blocks.append(v[n_dyn:n_dyn + ny_rows].reshape(o.N, o.p))
             if ndu_rows:
                 blocks.append(v[n_dyn + ny_rows:n_dyn + ny_rows + ndu_rows].reshape(o.N, o.m))
+            if ngin_rows:
+                o3 = n_dyn + ny_rows + ndu_rows
+                blocks.append(v[o3:o3 + ngin_rows].reshape(o.N, o.n_gin))
             return np.ascontiguousarray(np.hstack(blocks).reshape(-1)) if blocks else np.zeros(0)
         return per_stage(o.g_lb), per_stage(o.g_ub)
 
