@@ -64,6 +64,9 @@ __global__ void __launch_bounds__(MPCB_EVAL_BLOCK, MPCB_EVAL_MINBLOCKS) k_ocp_ev
 
 // KKT step: one thread per instance (small stage blocks, MPCB_KKT_LANES == 1) or one warp per instance with
 // per-warp scratch in shared memory (MPCB_KKT_LANES == 32)
+#ifndef MPCB_TGT_BLOCK
+#define MPCB_TGT_BLOCK 64       // threads per block of the one-thread-per-instance target solve
+#endif
 #ifndef KKT_WARPS
 #define KKT_WARPS 4
 #endif
@@ -593,7 +596,7 @@ int mpcb_stage_derivs(mpcb_handle_t h, const double* par, const double* w, const
 int mpcb_target(mpcb_handle_t h, const double* par_ss, double* wss, double* fss, int* status, int* iters, void* stream) {
 #if MPCB_HAS_TARGET
     TgtShared S; S.lbx = h->ss_lbx; S.ubx = h->ss_ubx; S.o = to_ipm(h->opts_ss);
-    { Prof p(h, (cudaStream_t)stream, KC_TARGET); k_target<<<nblk(h->B, 64), 64, 0, (cudaStream_t)stream>>>(h->B, par_ss, wss, fss, status, iters, S); }
+    { Prof p(h, (cudaStream_t)stream, KC_TARGET); k_target<<<nblk(h->B, MPCB_TGT_BLOCK), MPCB_TGT_BLOCK, 0, (cudaStream_t)stream>>>(h->B, par_ss, wss, fss, status, iters, S); }
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize((cudaStream_t)stream));
     prof_collect(h);

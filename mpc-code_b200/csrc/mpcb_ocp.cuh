@@ -355,9 +355,6 @@ MPCB_HD void ocp_eval_stage(OcpInst& I, const OcpShared& S, int k) {
 #ifndef MPCB_VEC_REC
 #define MPCB_VEC_REC 1
 #endif
-#ifndef MPCB_REC_STREAM
-#define MPCB_REC_STREAM 0       // 1: evict-first stores for the records, so that they do not displace the RK4 stage buffers in L2
-#endif
 #if MPCB_VEC_REC
     double r[REC_SZ];          // the record is assembled in registers and written out with 128-bit stores at the end
 #else
@@ -446,11 +443,7 @@ MPCB_HD void ocp_eval_stage(OcpInst& I, const OcpShared& S, int k) {
 #ifdef __CUDA_ARCH__
 #pragma unroll
         for (int i = 0; i < (R_PART + NPART + 1) / 2; ++i)
-#if MPCB_REC_STREAM
-            __stcs(reinterpret_cast<double2*>(rg_) + i, make_double2(r[2 * i], (2 * i + 1 < R_PART + NPART) ? r[2 * i + 1] : 0.0));
-#else
             reinterpret_cast<double2*>(rg_)[i] = make_double2(r[2 * i], (2 * i + 1 < R_PART + NPART) ? r[2 * i + 1] : 0.0);
-#endif
 #else
         for (int i = 0; i < R_PART + NPART; ++i) rg_[i] = r[i];
 #endif
