@@ -161,6 +161,8 @@ class CFunction:
         return "\n".join([head] + voids + lines + ["}"]) + "\n"
 
 
+BIG_FUNCTION_FLOPS = 3000          # generated functions above this size are not inlined
+
 EXPENSIVE_OPS = frozenset(("exp", "log", "sqrt", "sin", "cos", "tan", "tanh", "asin", "acos", "atan", "sinh", "cosh",
                            "pow", "atan2"))
 
@@ -228,6 +230,13 @@ def emit_header(guard: str, defines: Dict[str, object], functions: Sequence[CFun
            "#  else",
            "#    define MPCB_FN static inline",
            "#  endif",
+           "#endif",
+           "#ifndef MPCB_FN_BIG",
+           "#  ifdef __CUDACC__",
+           "#    define MPCB_FN_BIG static __host__ __device__ __noinline__",
+           "#  else",
+           "#    define MPCB_FN_BIG static __attribute__((noinline))",
+           "#  endif",
            "#endif", ""]
     if preamble:
         out.append(preamble)
@@ -240,7 +249,9 @@ def emit_header(guard: str, defines: Dict[str, object], functions: Sequence[CFun
         out.append("#define %s %s" % (k, v))
     out.append("")
     for f in functions:
-        out.append(f.source())
+        # very large bodies (dense models with many states) are compiled once instead of being inlined into every
+        # RK4 stage of every kernel: nvcc's time and the kernels' stack frames grow superlinearly otherwise
+        out.append(f.source("MPCB_FN_BIG" if f.flops > BIG_FUNCTION_FLOPS else "MPCB_FN"))
     out.append("#endif")
     return "\n".join(out) + "\n"
 
@@ -263,7 +274,7 @@ class CModule:
         self._ct = ctypes
         self.functions = {f.name: f for f in functions}
         src = emit_header("MPCB_GEN_%s_H" % name.upper(), {}, functions,
-                          preamble="#undef MPCB_FN\n#define MPCB_FN __attribute__((visibility(\"default\")))\n")
+                          preamble="#undef MPCB_FN\n#define MPCB_FN __attribute__((visibility(\"default\")))\n#undef MPCB_FN_BIG\n#define MPCB_FN_BIG MPCB_FN\n")
         digest = hashlib.sha256((src + " ".join(cflags)).encode()).hexdigest()[:16]
         os.makedirs(build_dir, exist_ok=True)
         c_path = os.path.join(build_dir, "%s_%s.c" % (name, digest))

@@ -68,7 +68,9 @@ __global__ void __launch_bounds__(MPCB_EVAL_BLOCK, MPCB_EVAL_MINBLOCKS) k_ocp_ev
 #define MPCB_TGT_BLOCK 64       // threads per block of the one-thread-per-instance target solve
 #endif
 #ifndef KKT_WARPS
-#define KKT_WARPS 4
+// warps (instances) per block of the KKT kernel: as many as fit the 48 kB of static shared memory, at most 4
+#define KKT_SCRATCH_BYTES ((int)sizeof(double) * KktScratch::total * (32 / MPCB_KKT_LANES))
+#define KKT_WARPS (4 * KKT_SCRATCH_BYTES <= 48 * 1024 ? 4 : (2 * KKT_SCRATCH_BYTES <= 48 * 1024 ? 2 : 1))
 #endif
 #if MPCB_KKT_LANES > 1
 __global__ void __launch_bounds__(32 * KKT_WARPS) k_ocp_kkt(OcpArgs a) {

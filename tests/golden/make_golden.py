@@ -28,7 +28,39 @@ from oracle.nlp import OcpNlp, TargetNlp  # noqa: E402
 REF = "/root/reference"
 
 
+def make_synthetic(names):
+    """Oracle solutions of members of the synthetic family (symbolic Hessians of the unrolled RK4 graph take minutes to
+    build for 8+ states - hence fixtures); members already in the file and not named are kept."""
+    import __graft_entry__ as entry
+    syn_path = os.path.join(HERE, "synthetic_oracle.npz")
+    syn = dict(np.load(syn_path)) if os.path.exists(syn_path) else {}        # members not named are kept
+    for name in names:
+        p_s, ss_s, ocp_s = entry._problem(name)
+        mod_s = cmodel.build(name, p_s, ocp_s, ss_s)
+        on_s = OcpNlp(ocp_s, mod_s)
+        rng_s = np.random.default_rng(5)
+        nxs, nus, Ns_ = p_s.nx, p_s.nu, p_s.N
+        nz_s = nxs + nus
+        w0s = np.zeros(ocp_s.nw)
+        pars, Ws, Fs, STs, ITs = [], [], [], [], []
+        for _ in range(4):
+            xh = rng_s.uniform(-1, 1, nxs)
+            par_s = np.concatenate([xh, np.zeros(nxs), np.zeros(nus), np.zeros(0), np.zeros(nus), [0.0], np.zeros(p_s.ny * nus),
+                                    np.zeros((p_s.npx + p_s.npy) * Ns_)])
+            lb, ub = ocp_s.w_lb.copy(), ocp_s.w_ub.copy(); lb[:nxs] = ub[:nxs] = xh
+            r = on_s.solve(w0s, par_s, lb, ub, opts=IpmOptions(max_iter=100))
+            pars.append(par_s); Ws.append(r.x); Fs.append(r.f); STs.append(r.status); ITs.append(r.iters)
+            print(name, r.return_status, r.iters, r.f)
+        syn.update({name + "_par": np.array(pars), name + "_w": np.array(Ws), name + "_f": np.array(Fs),
+                    name + "_status": np.array(STs), name + "_iters": np.array(ITs)})
+    np.savez_compressed(syn_path, **syn)
+
+
 def main():
+    only = [a for a in sys.argv if a.startswith("--only-synthetic=")]
+    if only:                                                      # python make_golden.py --only-synthetic=syn_12_4_20
+        make_synthetic(tuple(only[0].split("=", 1)[1].split(",")))
+        return
     ns = load_example(os.path.join(REF, "Ex_NMPC.py"))
     nl = load_example(os.path.join(REF, "Ex_LMPC_nlplant.py"))
     kat = dict(
@@ -120,29 +152,9 @@ def main():
     np.savez_compressed(os.path.join(HERE, "lmpc_oracle.npz"), **lin)
     # ---- synthetic family (BASELINE configs[4]): one mid-size member whose oracle (symbolic Hessian of the unrolled
     #      RK4 graph, 8 states) takes minutes to build - hence a fixture; smaller members are checked live by the tests
-    if "--synthetic" in sys.argv:
-        import __graft_entry__ as entry
-        syn = {}
-        for name in ("syn_8_3_50",):
-            p_s, ss_s, ocp_s = entry._problem(name)
-            mod_s = cmodel.build(name, p_s, ocp_s, ss_s)
-            on_s = OcpNlp(ocp_s, mod_s)
-            rng_s = np.random.default_rng(5)
-            nxs, nus, Ns_ = p_s.nx, p_s.nu, p_s.N
-            nz_s = nxs + nus
-            w0s = np.zeros(ocp_s.nw)
-            pars, Ws, Fs, STs, ITs = [], [], [], [], []
-            for _ in range(4):
-                xh = rng_s.uniform(-1, 1, nxs)
-                par_s = np.concatenate([xh, np.zeros(nxs), np.zeros(nus), np.zeros(0), np.zeros(nus), [0.0], np.zeros(p_s.ny * nus),
-                                        np.zeros((p_s.npx + p_s.npy) * Ns_)])
-                lb, ub = ocp_s.w_lb.copy(), ocp_s.w_ub.copy(); lb[:nxs] = ub[:nxs] = xh
-                r = on_s.solve(w0s, par_s, lb, ub, opts=IpmOptions(max_iter=100))
-                pars.append(par_s); Ws.append(r.x); Fs.append(r.f); STs.append(r.status); ITs.append(r.iters)
-                print(name, r.return_status, r.iters, r.f)
-            syn.update({name + "_par": np.array(pars), name + "_w": np.array(Ws), name + "_f": np.array(Fs),
-                        name + "_status": np.array(STs), name + "_iters": np.array(ITs)})
-        np.savez_compressed(os.path.join(HERE, "synthetic_oracle.npz"), **syn)
+    syn_args = [a for a in sys.argv if a.startswith("--synthetic")]       # --synthetic  or  --synthetic=syn_12_4_20,...
+    if syn_args:
+        make_synthetic(tuple(syn_args[0].split("=", 1)[1].split(",")) if "=" in syn_args[0] else ("syn_8_3_50",))
     print("wrote fixtures")
 
 
