@@ -117,4 +117,7 @@ def build(name, prob, ocp_spec=None, ss_spec=None) -> CModule:
         fns += ocp_functions(ocp_spec)
     if ss_spec is not None:
         fns += target_functions(ss_spec)
-    return CModule("orc_" + name, fns, BUILD_DIR, cflags=("-O1",))
+    # ORACLE_CFLAGS=-O0 for the largest members of the synthetic family: their unrolled second-derivative functions are
+    # tens of MB of C and gcc -O1 does not finish on them in an hour
+    cflags = tuple(os.environ.get("ORACLE_CFLAGS", "-O1").split())
+    return CModule("orc_" + name, fns, BUILD_DIR, cflags=cflags)

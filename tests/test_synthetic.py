@@ -1,7 +1,7 @@
 """BASELINE configs[4]: random stable nonlinear plants of several sizes (mpc_code_b200.synthetic).
 
-Small members are checked live against the oracle; the 8-state member against a committed fixture (its oracle
-needs ~8 minutes of symbolic differentiation).  Horizons above 64 exercise the multi-round lane loops."""
+Small members are checked live against the oracle, the 8-state member against a committed fixture (its oracle needs
+minutes of symbolic differentiation), the 12-state member against an independent single-shooting solution.  Horizons above 64 exercise the multi-round lane loops."""
 import os
 
 import numpy as np
@@ -35,13 +35,75 @@ def test_device_code_on_cpu_matches_oracle(name):
         assert np.abs(r.x - w[i]).max() < 1e-9 and abs(r.f - f[i]) <= 1e-10 * max(1.0, abs(r.f))
 
 
+def _single_shooting_reference(ns, xhat):
+    """Independent solution of the synthetic OCP: the plant matrices from the namespace, RK4 in NumPy, the states
+    eliminated (single shooting), exact gradients by the complex step, SciPy L-BFGS-B on |u| <= 1.  Shares no code
+    with the package below the three matrices."""
+    import scipy.optimize as sopt
+    m_ = ns["_synthetic"]
+    Ac, Bc, W, nx, nu, N = m_["Ac"], m_["Bc"], m_["W"], m_["nx"], m_["nu"], m_["N"]
+    h, Mx = 0.1, 4
+
+    def f(x, u):
+        return Ac @ x + Bc @ u + 0.1 * np.tanh(W @ x)
+
+    def rollout(U):
+        x = xhat.astype(U.dtype); J = 0.0; X = [x]
+        for k in range(N):
+            u = U[k * nu:(k + 1) * nu]
+            J = J + 0.5 * (x @ x + 0.1 * (u @ u))                # F_obj = 1/2 (x'Qx + u'Ru), Q = I, R = 0.1 I; no terminal cost
+            hs = h / Mx
+            for _ in range(Mx):
+                k1 = f(x, u); k2 = f(x + 0.5 * hs * k1, u); k3 = f(x + 0.5 * hs * k2, u); k4 = f(x + hs * k3, u)
+                x = x + hs / 6.0 * (k1 + 2 * k2 + 2 * k3 + k4)
+            X.append(x)
+        return J, X
+
+    def fun(U):
+        J, _ = rollout(U)
+        g = np.empty(U.size)
+        for i in range(U.size):
+            Uc = U.astype(complex); Uc[i] += 1e-30j
+            g[i] = rollout(Uc)[0].imag / 1e-30
+        return float(J), g
+    res = sopt.minimize(fun, np.zeros(N * nu), jac=True, method="L-BFGS-B", bounds=[(-1.0, 1.0)] * (N * nu),
+                        options=dict(maxiter=2000, ftol=1e-16, gtol=1e-11, maxcor=50))
+    J, X = rollout(res.x)
+    return res.x.reshape(N, nu), np.array(X), float(J)
+
+
+def _twelve_state_case():
+    b = _bundle("syn_12_4_20")
+    p = b.prob
+    xhat = np.random.default_rng(12).uniform(-1, 1, p.nx)
+    par = b.ocp_par(xhat, np.zeros(p.nx), np.zeros(p.nu), np.zeros(0))
+    return b, p, xhat, par
+
+
+def test_twelve_state_member_matches_an_independent_single_shooting_solution():
+    """12 states: the oracle's unrolled symbolic Hessian is 51 MB of C that gcc does not finish in an hour, so this
+    member is checked against an independent NumPy / SciPy solution instead (and its generated second-order products,
+    15 000 operations, are compiled out of line - codegen.BIG_FUNCTION_FLOPS)."""
+    b, p, xhat, par = _twelve_state_case()
+    w, f, st, it, _ = b.harness_ocp(par, np.zeros(p.nw))
+    U, X, J = _single_shooting_reference(p.ns, xhat)
+    nz = p.nx + p.nu
+    Ud = w[0, :nz * p.N].reshape(p.N, nz)[:, p.nx:]
+    Xd = np.vstack([w[0, :nz * p.N].reshape(p.N, nz)[:, :p.nx], w[0, nz * p.N:]])
+    assert st[0] == 0
+    assert np.abs(Ud - U).max() < 1e-5 and np.abs(Xd - X).max() < 1e-5
+    assert abs(f[0] - J) <= 1e-8 * max(1.0, abs(J))
+    assert np.abs(Ud).max() <= 1.0 + 1e-7
+
+
 def test_eight_state_member_matches_fixture_on_cpu():
-    b = _bundle("syn_8_3_50")
-    par = SYN["syn_8_3_50_par"]
+    name = "syn_8_3_50"
+    b = _bundle(name)
+    par = SYN[name + "_par"]
     w, f, st, it, _ = b.harness_ocp(par, np.zeros((par.shape[0], b.prob.nw)))
-    assert np.array_equal(st, SYN["syn_8_3_50_status"]) and np.array_equal(it, SYN["syn_8_3_50_iters"])
-    assert np.abs(w - SYN["syn_8_3_50_w"]).max() < 1e-9
-    assert np.all(np.abs(f - SYN["syn_8_3_50_f"]) <= 1e-10 * np.maximum(1.0, np.abs(SYN["syn_8_3_50_f"])))
+    assert np.array_equal(st, SYN[name + "_status"]) and np.array_equal(it, SYN[name + "_iters"])
+    assert np.abs(w - SYN[name + "_w"]).max() < 1e-9
+    assert np.all(np.abs(f - SYN[name + "_f"]) <= 1e-10 * np.maximum(1.0, np.abs(SYN[name + "_f"])))
 
 
 @pytest.mark.gpu
@@ -72,6 +134,23 @@ def test_gpu_matches_oracle(name):
     assert np.array_equal(solver.stats()["iter_count"].cpu().numpy(), ref_it)
     assert np.abs(sol["x"].cpu().numpy() - ref_w).max() < 1e-6
     assert np.all(np.abs(sol["f"].cpu().numpy() - ref_f) <= 1e-8 * np.maximum(1.0, np.abs(ref_f)))
+
+
+@pytest.mark.gpu
+def test_gpu_twelve_state_member():
+    from mpc_code_b200.mpc_loop import CompiledProblem
+    from mpc_code_b200.solvers import BatchedNlpSolver, MpcbHandle
+    b, p, xhat, par = _twelve_state_case()
+    U, X, J = _single_shooting_reference(p.ns, xhat)
+    cp = CompiledProblem(p, "syn_12_4_20")
+    h = MpcbHandle(cp.library, 2, dict(max_iter=100), dict(max_iter=100))
+    solver = BatchedNlpSolver("ocp", cp.ocp_spec).attach(h)
+    sol = solver(x0=np.zeros((2, p.nw)), p=np.tile(par, (2, 1)))
+    w = sol["x"].cpu().numpy()
+    nz = p.nx + p.nu
+    assert np.all(solver.stats()["status"].cpu().numpy() == 0) and np.array_equal(w[0], w[1])
+    assert np.abs(w[0, :nz * p.N].reshape(p.N, nz)[:, p.nx:] - U).max() < 1e-5
+    assert abs(float(sol["f"][0]) - J) <= 1e-8 * max(1.0, abs(J))
 
 
 @pytest.mark.gpu
