@@ -1,7 +1,8 @@
 """BASELINE configs[4]: random stable nonlinear plants of several sizes (mpc_code_b200.synthetic).
 
-Small members are checked live against the oracle, the 8-state member against a committed fixture (its oracle needs
-minutes of symbolic differentiation), the 12-state member against an independent single-shooting solution.  Horizons above 64 exercise the multi-round lane loops."""
+Small members are checked live against the oracle, the 8- and 12-state members against committed fixtures (their
+oracles need minutes of symbolic differentiation and compilation), the 12-state member also against an independent
+single-shooting solution.  Horizons above 64 exercise the multi-round lane loops."""
 import os
 
 import numpy as np
@@ -81,9 +82,8 @@ def _twelve_state_case():
 
 
 def test_twelve_state_member_matches_an_independent_single_shooting_solution():
-    """12 states: the oracle's unrolled symbolic Hessian is 51 MB of C that gcc does not finish in an hour, so this
-    member is checked against an independent NumPy / SciPy solution instead (and its generated second-order products,
-    15 000 operations, are compiled out of line - codegen.BIG_FUNCTION_FLOPS)."""
+    """12 states (generated second-order products of 15 000 operations, compiled out of line -
+    codegen.BIG_FUNCTION_FLOPS): besides the oracle fixture, an independent NumPy / SciPy solution of the same OCP."""
     b, p, xhat, par = _twelve_state_case()
     w, f, st, it, _ = b.harness_ocp(par, np.zeros(p.nw))
     U, X, J = _single_shooting_reference(p.ns, xhat)
@@ -96,8 +96,10 @@ def test_twelve_state_member_matches_an_independent_single_shooting_solution():
     assert np.abs(Ud).max() <= 1.0 + 1e-7
 
 
-def test_eight_state_member_matches_fixture_on_cpu():
-    name = "syn_8_3_50"
+@pytest.mark.parametrize("name", ["syn_8_3_50", "syn_12_4_20"])
+def test_larger_members_match_oracle_fixtures_on_cpu(name):
+    """Fixtures: tests/golden/make_golden.py --only-synthetic=<name> (the 12-state oracle needs ORACLE_CFLAGS=-O0 and
+    23 minutes of gcc)."""
     b = _bundle(name)
     par = SYN[name + "_par"]
     w, f, st, it, _ = b.harness_ocp(par, np.zeros((par.shape[0], b.prob.nw)))
@@ -107,13 +109,13 @@ def test_eight_state_member_matches_fixture_on_cpu():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["syn_2_1_20", "syn_4_2_70", "syn_8_3_50"])
+@pytest.mark.parametrize("name", ["syn_2_1_20", "syn_4_2_70", "syn_8_3_50", "syn_12_4_20"])
 def test_gpu_matches_oracle(name):
     from mpc_code_b200.mpc_loop import CompiledProblem
     from mpc_code_b200.solvers import BatchedNlpSolver, MpcbHandle
     b = _bundle(name)
     p = b.prob
-    if name == "syn_8_3_50":
+    if name in ("syn_8_3_50", "syn_12_4_20"):
         par = SYN[name + "_par"]; ref_w, ref_f, ref_it = SYN[name + "_w"], SYN[name + "_f"], SYN[name + "_iters"]
     else:
         from oracle.ipm import IpmOptions
