@@ -247,7 +247,7 @@ MPCB_HD void ocp_init_stage(OcpInst& I, const OcpShared& S, int k) {
 #if NG > 0
         double d[ND + 1], px[NPX + 1], py[NPY + 1], t0, Y[NG];
         stage_params(I.par, k, d, px, py, &t0);
-        ocp_out(w + k * NZA, w + k * NZA + NXA, I.par, py, Y);
+        ocp_out(w + k * NZA, w + k * NZA + NXA, I.par, px, py, Y);
         for (int i = 0; i < NG; ++i) {
             const double lo = S.lbg[k * NG + i], hi = S.ubg[k * NG + i];
             const double lor = fin(lo) ? rlo(lo, rf) : lo, hir = fin(hi) ? rhi(hi, rf) : hi;
@@ -397,7 +397,7 @@ MPCB_HD void ocp_eval_stage(OcpInst& I, const OcpShared& S, int k) {
         double Y[NG], JY[NG * NZA], HY[NZAP], mult[NG];
 #pragma unroll
         for (int i = 0; i < NG; ++i) mult[i] = I.ym[k * NG + i];
-        ocp_out_d(z, u, I.par, py, mult, Y, JY, HY);
+        ocp_out_d(z, u, I.par, px, py, mult, Y, JY, HY);
 #if !MPCB_OUT_LINEAR
 #pragma unroll
         for (int j = 0; j < NZA; ++j)
@@ -1046,7 +1046,7 @@ MPCB_HD void ocp_trial_stage(OcpInst& I, const OcpShared& S, int k) {
 #if NG > 0
     {
         double Y[NG];
-        ocp_out(z, u, I.par, py, Y);
+        ocp_out(z, u, I.par, px, py, Y);
         for (int i = 0; i < NG; ++i) {
             const int gi = k * NG + i;
             const double st_ = I.s[gi] + al * I.ds[gi];

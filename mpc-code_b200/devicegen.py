@@ -222,13 +222,11 @@ def generate_header(prob, ss_spec, ocp_spec, opts: Optional[Dict] = None) -> Dic
             if not o.DuFree:
                 rows.append(o.DU)
             if o.G is not None:                         # user stage inequalities, after the Y and DU rows
-                if _depends_on(o.G, pxk):
-                    raise NotImplementedError("User_g_ineq depending on the state-map parameters px is not on the device path")
                 rows.append(o.G)
             R = vertcat(*rows)
             mult = SX.sym("mult", n_rows)
             Hy, _ = hessian(mtimes(mult.T, R), zz)
-            ins_y = [("Z", Z), ("U", U), ("par", par), ("pyk", pyk)]
+            ins_y = [("Z", Z), ("U", U), ("par", par), ("pxk", pxk), ("pyk", pyk)]
             fns.append(CFunction("ocp_out", ins_y, [("Y", R)]))
             fns.append(CFunction("ocp_out_d", ins_y + [("mult", mult)],
                                  [("Y", R), ("JY", jacobian(R, zz)), ("HY", tril_pack(Hy))]))
