@@ -280,11 +280,18 @@ class CModule:
         c_path = os.path.join(build_dir, "%s_%s.c" % (name, digest))
         so_path = os.path.join(build_dir, "%s_%s.so" % (name, digest))
         if not os.path.exists(so_path):
-            with open(c_path, "w") as fh:
+            # several processes may get here at once (the bench's oracle workers): every one compiles its OWN copy of the
+            # source and publishes the result by an atomic rename - a shared .c file would be truncated under a running gcc
+            tmp_c = "%s.tmp%d.c" % (c_path[:-2], os.getpid())
+            tmp_so = so_path + ".tmp%d" % os.getpid()
+            with open(tmp_c, "w") as fh:
                 fh.write(src)
-            tmp = so_path + ".tmp%d" % os.getpid()
-            subprocess.run(["gcc", "-shared", "-fPIC", "-std=c99", *cflags, "-o", tmp, c_path, "-lm"], check=True)
-            os.replace(tmp, so_path)
+            try:
+                subprocess.run(["gcc", "-shared", "-fPIC", "-std=c99", *cflags, "-o", tmp_so, tmp_c, "-lm"], check=True)
+                os.replace(tmp_so, so_path)
+            finally:
+                if os.path.exists(tmp_c):
+                    os.remove(tmp_c)
         self.so_path = so_path
         self._lib = ctypes.CDLL(so_path)
         self._dp = ctypes.POINTER(ctypes.c_double)
