@@ -112,14 +112,14 @@ def run_reference(args):
     pool.close()
     value = float(np.mean(samples))
     sample = "%d instances x 1 closed-loop step per bench step, one process per core" % n_inst
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "Ex_NMPC CSTR NMPC+EKF, N=50, Mx=10; CPU oracle port (dense IPM, not IPOPT)", "batch": n_inst},
         "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0}))
+        "gpu_launches": 0})
 
 
 # ---------------------------------------------------------------------------------------------
@@ -370,7 +370,7 @@ def run_gpu(args):
         "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
         "solver_stats": stats,
     }
-    print(json.dumps(out))
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
 
@@ -383,6 +383,17 @@ def cp_ws_bytes(cp):
     return 8 * (d.N * (rec + 20 + 4 * d.nx + 6 * d.ng) + 5 * d.nw + d.npar)
 
 
+_JSON_FD = None
+
+
+def emit(record):
+    line = (json.dumps(record) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(line.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, line)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -391,6 +402,12 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # stdout carries exactly ONE line, the JSON record: everything else that libraries write to file descriptor 1 (NCCL
+    # prints its version banner there) is sent to stderr, and the record goes to the saved descriptor at the end
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
