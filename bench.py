@@ -48,8 +48,30 @@ def _workload(prob, B, nsteps, rank=0):
 
 
 # ---------------------------------------------------------------------------------------------
-# CPU arm (the oracle port): used for `cpu_baseline` and for `--impl reference`
+# CPU arm: used for `cpu_baseline` and for `--impl reference`.  Two implementations are timed on the box's host cores,
+# each on a bounded sample of the SAME workload (same x0 distribution and noise), each over CONSECUTIVE closed-loop steps
+# of every instance after that instance's own cold-start steps (the first step has a different warm start,
+# MPC_code.py:740-756, and more iterations):
+#   * "cxx"   - oracle/cxx_loop.cpp: the host build (g++ -O3 -march=native -fopenmp) of this repo's solver sources,
+#               OpenMP over instances on all cores.  Same algorithm as the kernels, ~15x faster than the NumPy port: the
+#               strongest CPU implementation available here, hence the one the reference arm reports.
+#   * "numpy" - oracle/closed_loop.py: the independent NumPy/LAPACK restatement (dense KKT), one process per core.
+# Neither is IPOPT: CasADi/IPOPT cannot be installed here or on the GPU box (profiles/r02_casadi_probe.txt).
 # ---------------------------------------------------------------------------------------------
+CPU_WARM_STEPS = 5            # per-instance cold-start steps excluded from the CPU timings
+
+
+def cxx_throughput(n_inst, nsteps, rank=0):
+    """(instance-steps/s, threads, wall seconds) of the C++/OpenMP closed loop for `nsteps` timed steps per instance."""
+    from oracle.cxx_baseline import CxxLoop, range_bounds_of
+    prob, ss, ocp = _problem()
+    loop = CxxLoop("nmpc_cstr", prob, ss, ocp, range_bounds_of(ocp))
+    x0, noise = _workload(prob, n_inst, CPU_WARM_STEPS + nsteps, rank)
+    t0 = time.time()
+    v, r = loop.throughput(x0, noise, CPU_WARM_STEPS)
+    return v, int(r["threads"]), time.time() - t0
+
+
 _ORACLE = {}
 
 
@@ -64,34 +86,54 @@ def _oracle_init():
 
 
 def _oracle_worker(args):
-    x0, noise, nsteps = args
-    t0 = time.time()
-    rec = _ORACLE["loop"].run(Nsim=nsteps, x0_p=x0, x0_m=x0, noise=noise)
-    return time.time() - t0, int(np.sum(rec["ITER_DYN"]))
+    """Closed loop of one instance; returns the seconds spent in the steps after the cold-start ones."""
+    x0, noise, nwarm = args
+    loop = _ORACLE["loop"]
+    t_mark = []
+    rec = loop.run(Nsim=noise.shape[0], x0_p=x0, x0_m=x0, noise=noise, on_step=lambda k: t_mark.append(time.time()))
+    t_end = time.time()
+    return t_end - t_mark[nwarm], int(np.sum(rec["ITER_DYN"]))
 
 
 class OraclePool:
-    """Worker processes (spawned, so no BLAS thread state is inherited), each holding the CPU oracle."""
+    """Worker processes (spawned, so no BLAS thread state is inherited), each holding the NumPy oracle."""
 
     def __init__(self, cores):
         self.cores = cores
         self.pool = mp.get_context("spawn").Pool(cores, initializer=_oracle_init)
         prob, _, _ = _problem()
         x0, noise = _workload(prob, cores, 1)
-        self.pool.map(_oracle_worker, [(x0[i], noise[:, i, :], 1) for i in range(cores)], chunksize=1)   # warm up
+        self.pool.map(_oracle_worker, [(x0[i], noise[:, i, :], 0) for i in range(cores)], chunksize=1)   # build / import
         self.prob = prob
 
     def throughput(self, n_inst, nsteps):
-        """Closed-loop instance-steps per second over all workers."""
-        x0, noise = _workload(self.prob, n_inst, nsteps)
-        jobs = [(x0[i], noise[:, i, :], nsteps) for i in range(n_inst)]
+        """Closed-loop instance-steps per second over all workers (timed steps / per-core busy time)."""
+        x0, noise = _workload(self.prob, n_inst, CPU_WARM_STEPS + nsteps)
+        jobs = [(x0[i], noise[:, i, :], CPU_WARM_STEPS) for i in range(n_inst)]
         t0 = time.time()
-        self.pool.map(_oracle_worker, jobs, chunksize=1)
+        res = self.pool.map(_oracle_worker, jobs, chunksize=1)
         wall = time.time() - t0
-        return n_inst * nsteps / wall, wall
+        busy = sum(r[0] for r in res) / self.cores
+        return n_inst * nsteps / busy, wall
 
     def close(self):
         self.pool.close(); self.pool.join()
+
+
+def cpu_baselines(cores, cxx_inst_per_core=8, cxx_steps=40, numpy_steps=20):
+    """The two CPU figures of one bench line (bounded: ~10 s of C++ work, ~10 s of NumPy work)."""
+    v, threads, wall = cxx_throughput(cxx_inst_per_core * cores, cxx_steps)
+    cxx = {"value": v, "unit": "steps/s", "cores": threads, "kind": "port",
+           "sample": "%d instances x %d consecutive closed-loop steps after %d cold-start steps each, same workload; host build of "
+                     "this repo's solver sources (same algorithm, C++, g++ -O3 -fopenmp over instances; %.1f s); not IPOPT"
+                     % (cxx_inst_per_core * cores, cxx_steps, CPU_WARM_STEPS, wall)}
+    pool = OraclePool(cores)
+    v2, wall2 = pool.throughput(cores, numpy_steps)
+    pool.close()
+    npy = {"value": v2, "unit": "steps/s", "cores": cores, "kind": "port",
+           "sample": "%d instances x %d consecutive closed-loop steps after %d cold-start steps each, one process per core (%.1f s); "
+                     "independent NumPy/LAPACK dense-KKT oracle (the parity checker), not IPOPT" % (cores, numpy_steps, CPU_WARM_STEPS, wall2)}
+    return cxx, npy
 
 
 def run_reference(args):
@@ -99,27 +141,46 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n_inst = cores                                   # one instance per core per step
-    pool = OraclePool(cores)
-    samples = []
+    n_inst, nsteps = 4 * cores, 20          # per bench step: every instance runs 5 cold-start + 20 timed consecutive steps
+    samples, threads = [], cores
     for _ in range(args.warmup):
-        pool.throughput(n_inst, 1)
+        cxx_throughput(n_inst, nsteps)
     t0 = time.time()
     for _ in range(args.steps):
-        v, _ = pool.throughput(n_inst, 1)
+        v, threads, _ = cxx_throughput(n_inst, nsteps)
         samples.append(v)
     wall = time.time() - t0
-    pool.close()
     value = float(np.mean(samples))
-    sample = "%d instances x 1 closed-loop step per bench step, one process per core" % n_inst
+    sample = ("per bench step: %d instances x %d consecutive closed-loop steps after %d cold-start steps each; host build of this "
+              "repo's solver sources (same algorithm, C++, OpenMP over instances); not IPOPT" % (n_inst, nsteps, CPU_WARM_STEPS))
+    pool = OraclePool(cores)
+    v2, wall2 = pool.throughput(cores, 20)
+    pool.close()
     emit({
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": 0, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "Ex_NMPC CSTR NMPC+EKF, N=50, Mx=10; CPU oracle port (dense IPM, not IPOPT)", "batch": n_inst},
-        "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": _config(1, n_inst, None),
+        "cpu_baseline": {"value": value, "unit": "steps/s", "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline_numpy": {"value": v2, "unit": "steps/s", "cores": cores, "kind": "port",
+                               "sample": "%d instances x 20 consecutive steps after %d cold-start steps, one process per core "
+                                         "(%.1f s); independent NumPy/LAPACK oracle" % (cores, CPU_WARM_STEPS, wall2)},
         "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0})
+
+
+def _config(world, batch_per_rank, groups, extra=None):
+    """`config` of both arms: the same workload description (the arms differ in the sample size they time)."""
+    c = {"workload": "Ex_NMPC (configs[1]): CSTR NMPC + EKF + target, N=50, Mx=10, closed loop with plant and measurement "
+                     "noise; x0 perturbed 2%%/0.2%%/2%% (seed %d)" % SEED_X0,
+         "batch_per_gpu": BATCH_PER_GPU, "global_batch": world * BATCH_PER_GPU,
+         "parallelism": "instances sharded, %d rank(s)" % world}
+    if batch_per_rank != BATCH_PER_GPU:
+        c["sample_instances"] = batch_per_rank
+    if groups is not None:
+        c["instance_groups_per_gpu"] = groups
+    c.update(extra or {})
+    return c
 
 
 # ---------------------------------------------------------------------------------------------
@@ -186,6 +247,10 @@ def run_gpu(args):
     import torch.distributed as dist
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit("bench.py --gpus %d needs %d ranks: launch it with `python -m torch.distributed.run --nnodes=1 "
+                         "--nproc-per-node %d --master-addr 127.0.0.1 bench.py --gpus %d ...` (WORLD_SIZE is %d)"
+                         % (args.gpus, args.gpus, args.gpus, args.gpus, world))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -342,32 +407,23 @@ def run_gpu(args):
         "line_search_trials_per_iteration": prof["trial_instances"] / max(prof["eval_instances"], 1),
     }
 
-    # ---------------- CPU baseline beside it (bounded sample) ----------------
-    cpu_baseline = None
+    # ---------------- CPU baselines beside it (bounded samples) ----------------
+    cpu_baseline = cpu_numpy = None
     if world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        pool = OraclePool(cores)
-        v, wall = pool.throughput(cores, 60)
-        pool.close()
-        cpu_baseline = {"value": v, "unit": "steps/s", "cores": cores, "kind": "port",
-                        "sample": "%d instances x 60 closed-loop steps of the same workload, one process per core (%.1f s); "
-                                  "dense-KKT oracle port, not IPOPT" % (cores, wall)}
+        cpu_baseline, cpu_numpy = cpu_baselines(os.cpu_count() or 1)
     clocks = _parse_clocks(clock_file, local, windows)
     out = {
         "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": elapsed_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": "Ex_NMPC (configs[1]): CSTR NMPC + EKF + target, N=50, Mx=10, closed loop with plant and "
-                               "measurement noise; %d instances per GPU, x0 perturbed 2%%/0.2%%/2%% (seed %d)" % (B, SEED_X0),
-                   "batch_per_gpu": B, "global_batch": world * B, "parallelism": "instances sharded, %d rank(s)" % world,
-                   "instance_groups_per_gpu": groups,
-                   "cache": "per-step working set %.0f MB per GPU > 126 MB L2 (no flush needed)" % (B * cp_ws_bytes(cp) / 1e6)},
+        "config": _config(world, B, groups, {"cache": "per-step working set %.0f MB per GPU > 126 MB L2 (no flush needed)"
+                                                      % (B * cp_ws_bytes(cp) / 1e6)}),
         "p50_step_latency_ms": float(np.median(step_ms)), "p99_step_latency_ms": float(np.percentile(step_ms, 99)),
         "slowest_steps": [[int(i), float(step_ms[i])] for i in np.argsort(-step_ms)[:3]],
         "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": B * prob.ny * 8, "d2h_bytes_per_step": B * prob.nu * 8,
                 "replay_max_abs_du": replay_err},
         "gpu_launches": int(launches),
-        "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "cpu_baseline_numpy": cpu_numpy, "clocks": clocks,
         "solver_stats": stats,
     }
     emit(out)

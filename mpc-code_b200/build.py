@@ -51,9 +51,11 @@ def build_library(name: str, prob, ss_spec, ocp_spec, verbose: bool = False, ext
     so_path = os.path.join(BUILD_DIR, "libmpcb_%s_%s.so" % (name, digest))
     header = os.path.join(work, "mpcb_model.h")
     os.makedirs(work, exist_ok=True)
-    if not os.path.exists(header):
-        with open(header, "w") as fh:
+    if not os.path.exists(header):          # published atomically: several ranks may start on a cold _build at once
+        tmp_h = header + ".tmp%d" % os.getpid()
+        with open(tmp_h, "w") as fh:
             fh.write(gen["text"])
+        os.replace(tmp_h, header)
     if not os.path.exists(so_path):
         tmp = so_path + ".tmp%d" % os.getpid()
         cmd = [_nvcc(), *NVCC_FLAGS, *extra_flags, "-I", work, "-I", CSRC, "-I", INCLUDE,

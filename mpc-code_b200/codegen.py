@@ -36,10 +36,12 @@ class CFunction:
     def __init__(self, name: str, inputs: Sequence[Tuple[str, SX]], outputs: Sequence[Tuple[str, SX]],
                  skip_zero_outputs: bool = False, shared_reciprocals: bool = False, cache_in=None):
         self.name = name
-        # cache_in = (argument name, entries): values of expensive sub-expressions computed by ANOTHER generated function
-        # at the same point and handed in through an extra ``const double*`` argument instead of being recomputed
-        # (see `expensive_entries`).  entries[i] = ("node", expr) -> arg[i] replaces that node;
+        # cache_in = [(argument name, entries), ...]: values of expensive sub-expressions computed by ANOTHER generated
+        # function at the same point and handed in through extra ``const double*`` arguments instead of being
+        # recomputed (see `expensive_entries`).  entries[i] = ("node", expr) -> arg[i] replaces that node;
         # ("recip", den) -> arg[i] is 1/den and replaces the shared reciprocal of that denominator.
+        if cache_in is not None and isinstance(cache_in, tuple):
+            cache_in = [cache_in]
         self.cache_in = cache_in
         self.inputs = [(n, v if isinstance(v, SX) else SX(v)) for n, v in inputs]
         self.outputs = [(n, v if isinstance(v, SX) else SX(v)) for n, v in outputs]
@@ -58,8 +60,8 @@ class CFunction:
     # -- text ------------------------------------------------------------------
     def signature(self, qualifier="MPCB_FN") -> str:
         args = ["const double* %s" % n for n, _ in self.inputs]
-        if self.cache_in is not None:
-            args.append("const double* %s" % self.cache_in[0])
+        for cname, _ in (self.cache_in or ()):
+            args.append("const double* %s" % cname)
         args += ["double* %s" % n for n, _ in self.outputs]
         return "%s void %s(%s)" % (qualifier, self.name, ", ".join(args))
 
@@ -77,12 +79,12 @@ class CFunction:
         recips: Dict[int, str] = {}
         cut_nodes: Dict[int, str] = {}
         if self.cache_in is not None:
-            cname, entries = self.cache_in
-            for i, (kind, e) in enumerate(entries):
-                if kind == "node":
-                    cut_nodes[e.uid] = "%s[%d]" % (cname, i)
-                else:
-                    recips[e.uid] = "%s[%d]" % (cname, i)
+            for cname, entries in self.cache_in:
+                for i, (kind, e) in enumerate(entries):
+                    if kind == "node":
+                        cut_nodes[e.uid] = "%s[%d]" % (cname, i)
+                    else:
+                        recips[e.uid] = "%s[%d]" % (cname, i)
             live = live_nodes(self._flat_out, set(cut_nodes), set(recips) if self.shared_reciprocals else set())
             order = [n for n in order if n.uid in live]
         tcount = 0
@@ -107,7 +109,7 @@ class CFunction:
                 else:
                     if den.uid not in recips:
                         rname = "r%d" % len(recips)
-                        lines.append("  const double %s = 1.0 / %s;" % (rname, a[1]))
+                        lines.append("  const double %s = MPCB_RCP(%s);" % (rname, a[1]))
                         recips[den.uid] = rname
                     rhs = recips[den.uid] if n.args[0] is S.ONE else "%s * %s" % (a[0], recips[den.uid])
             elif op in _INFIX:
@@ -156,6 +158,8 @@ class CFunction:
                     continue
                 lines.append("  %s[%d] = %s;" % (name, i, ref[e.uid]))
         unused = [n for n, v in self.inputs if not any(e.uid in used_inputs for e in v.elements())]
+        unused += [cname for cname, _ in (self.cache_in or ())]        # a cache argument may go unused in this function
+        unused += [n for n, v in self.outputs if v.numel() == 0]
         head = self.signature(qualifier) + " {"
         voids = ["  (void)%s;" % n for n in unused]
         return "\n".join([head] + voids + lines + ["}"]) + "\n"
@@ -240,7 +244,7 @@ def emit_header(guard: str, defines: Dict[str, object], functions: Sequence[CFun
            "#endif", ""]
     if preamble:
         out.append(preamble)
-    out += ["#ifndef MPCB_EXP", "#define MPCB_EXP exp", "#endif", ""]
+    out += ["#ifndef MPCB_EXP", "#define MPCB_EXP exp", "#endif", "#ifndef MPCB_RCP", "#define MPCB_RCP(x) (1.0 / (x))", "#endif", ""]
     for k, v in defines.items():
         if isinstance(v, bool):
             v = int(v)

@@ -147,6 +147,8 @@ def build_ocp_spec(xSX, uSX, ySX, dSX, tSX, pxSX, pySX, n, m, p, nd, npx, npy, n
         w_lb[k * nxu - m:k * nxu] = umin_v; w_ub[k * nxu - m:k * nxu] = umax_v
     ng = n * (N + 1) + (n if TermCons is True else 0)
     ng1 = 0 if yFree else p * N
+    if ContForm is True:
+        DuFree = True                  # the ContForm branch never forms DU_k: no g2 rows, Dumin/Dumax ignored (Control_Calc.py:153-158)
     ng2 = 0 if DuFree else m * N
     ng4 = 0 if G is None else G.numel() * N
     g_lb = np.zeros(ng + ng1 + ng2 + ng4); g_ub = np.zeros(ng + ng1 + ng2 + ng4)

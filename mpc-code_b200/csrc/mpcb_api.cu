@@ -22,7 +22,10 @@ enum { KC_OCP_INIT = 0, KC_OCP_EVAL = 1, KC_OCP_KKT = 2, KC_OCP_TRIAL = 3, KC_OC
 #define MPCB_EVAL_BLOCK 128
 #endif
 #ifndef MPCB_EVAL_MINBLOCKS
-#define MPCB_EVAL_MINBLOCKS 3
+// 2 blocks of 128 threads per SM: 254 registers per thread, no spills.  Measured on B200 (Ex_NMPC, profiles/r02_variants_*.txt):
+// 3 blocks (168 registers, the sweeps' matrices spilling) 32.4 ms of evaluation per 10 steps, 2 blocks 25.0, 9 blocks of 32
+// threads at 224 registers 25.2, 11 at 184 registers 29.5 - occupancy beyond 8 warps does not pay for the spills.
+#define MPCB_EVAL_MINBLOCKS 2
 #endif
 
 #ifndef MPCB_FLOPS_TABLE
@@ -52,14 +55,27 @@ __global__ void __launch_bounds__(128) k_ocp_init(OcpArgs a) {
     ocp_init_stage(I, a.S, k);
 }
 
-__global__ void __launch_bounds__(MPCB_EVAL_BLOCK, MPCB_EVAL_MINBLOCKS) k_ocp_eval(OcpArgs a) {
+// The sub-step records of the RK4 sweeps (EVAL_RK_DOUBLES per thread) live in shared memory when MINBLOCKS blocks of
+// them fit one SM (227 kB; Ex_NMPC: 70 doubles x 128 threads x 2 blocks = 140 kB), otherwise in thread-local memory.
+#ifndef MPCB_EVAL_SMEM
+#define MPCB_EVAL_SMEM ((EVAL_RK_DOUBLES) > 0 && \
+                        ((size_t)(EVAL_RK_DOUBLES) * 8 * MPCB_EVAL_BLOCK + 1024) * MPCB_EVAL_MINBLOCKS <= 232448)
+#endif
+#define EVAL_SMEM_BYTES (MPCB_EVAL_SMEM ? (size_t)(EVAL_RK_DOUBLES) * 8 * MPCB_EVAL_BLOCK : 0)
+#ifdef MPCB_EVAL_MAXNREG
+#define EVAL_BOUNDS __maxnreg__(MPCB_EVAL_MAXNREG)
+#else
+#define EVAL_BOUNDS __launch_bounds__(MPCB_EVAL_BLOCK, MPCB_EVAL_MINBLOCKS)
+#endif
+__global__ void EVAL_BOUNDS k_ocp_eval(OcpArgs a) {
+    extern __shared__ double eval_smem[];
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int inst = tid / NH, k = tid % NH;
     if (inst >= a.B) return;
     if (a.st[inst].state != ST_EVAL) return;
     if (k == 0) atomicAdd(a.counters, 1ULL);
     OcpInst I = ocp_view(a, inst);
-    ocp_eval_stage(I, a.S, k);
+    ocp_eval_stage<MPCB_EVAL_SMEM>(I, a.S, k, RkBuf{eval_smem + threadIdx.x, MPCB_EVAL_BLOCK});
 }
 
 // KKT step: one thread per instance (small stage blocks, MPCB_KKT_LANES == 1) or one warp per instance with
@@ -125,8 +141,9 @@ __global__ void k_ocp_output(OcpArgs a, double* f, int* status, int* iters) {
 }
 
 // stage derivatives alone (mpcb_stage_derivs)
-__global__ void __launch_bounds__(MPCB_EVAL_BLOCK, MPCB_EVAL_MINBLOCKS) k_stage_derivs(int B, const double* par, const double* w, const double* lam,
+__global__ void EVAL_BOUNDS k_stage_derivs(int B, const double* par, const double* w, const double* lam,
                                                       double* A, double* Bm, double* c, double* H) {
+    extern __shared__ double eval_smem[];
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int inst = tid / NH, k = tid % NH;
     if (inst >= B) return;
@@ -137,7 +154,7 @@ __global__ void __launch_bounds__(MPCB_EVAL_BLOCK, MPCB_EVAL_MINBLOCKS) k_stage_
     stage_params(pi, k, d, px, py, &t0);
     double xn[NX], Al[NX * NX], Bl[NX * NU], Hp[NZP];
     for (int i = 0; i < NZP; ++i) Hp[i] = 0.0;
-    dyn_full(x, u, d, px, t0, l, xn, Al, Bl, Hp);
+    dyn_full<(MPCB_EVAL_SMEM && MPCB_DYN_RK4 && !MPCB_CONTFORM)>(x, u, d, px, t0, l, xn, Al, Bl, Hp, RkBuf{eval_smem + threadIdx.x, MPCB_EVAL_BLOCK});
     const size_t s = (size_t)inst * NH + k;
     for (int i = 0; i < NX * NX; ++i) A[s * NX * NX + i] = Al[i];
     for (int i = 0; i < NX * NU; ++i) Bm[s * NX * NU + i] = Bl[i];
@@ -464,6 +481,10 @@ int mpcb_create(int batch, const mpcb_opts_t* oss, const mpcb_opts_t* odyn, mpcb
     CK(cudaMalloc(&h->st, sizeof(InstState) * (size_t)batch));
     CK(cudaMalloc(&h->lbx, sizeof(double) * NWI)); CK(cudaMalloc(&h->ubx, sizeof(double) * NWI));
     CK(cudaMalloc(&h->lbg, sizeof(double) * (NH * NGS))); CK(cudaMalloc(&h->ubg, sizeof(double) * (NH * NGS)));
+    if (EVAL_SMEM_BYTES > 0) {
+        CK(cudaFuncSetAttribute(k_ocp_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EVAL_SMEM_BYTES));
+        CK(cudaFuncSetAttribute(k_stage_derivs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EVAL_SMEM_BYTES));
+    }
 #endif
     h->ss_lbx = h->ss_ubx = nullptr;
 #if MPCB_HAS_TARGET
@@ -555,7 +576,7 @@ int mpcb_ocp(mpcb_handle_t h, const double* par, double* w, double* f, int* stat
     const int check_every = 2;
     while (ticks < max_ticks) {
         for (int c = 0; c < check_every; ++c) {
-            { Prof p(h, s, KC_OCP_EVAL); k_ocp_eval<<<nblk(nst, MPCB_EVAL_BLOCK), MPCB_EVAL_BLOCK, 0, s>>>(a); }
+            { Prof p(h, s, KC_OCP_EVAL); k_ocp_eval<<<nblk(nst, MPCB_EVAL_BLOCK), MPCB_EVAL_BLOCK, EVAL_SMEM_BYTES, s>>>(a); }
             { Prof p(h, s, KC_OCP_KKT); k_ocp_kkt<<<KKT_GRID(h->B), 0, s>>>(a); }
             { Prof p(h, s, KC_OCP_TRIAL); k_ocp_trial<<<nblk(nst, bs), bs, 0, s>>>(a); }
             if (c == check_every - 1) CK(cudaMemsetAsync(h->n_active, 0, sizeof(int), s));
@@ -586,7 +607,7 @@ int mpcb_ocp(mpcb_handle_t h, const double* par, double* w, double* f, int* stat
 int mpcb_stage_derivs(mpcb_handle_t h, const double* par, const double* w, const double* lam,
                       double* A, double* Bm, double* c, double* H, void* stream) {
 #if MPCB_HAS_OCP
-    { Prof p(h, (cudaStream_t)stream, KC_OTHER); k_stage_derivs<<<nblk((long)h->B * NH, MPCB_EVAL_BLOCK), MPCB_EVAL_BLOCK, 0, (cudaStream_t)stream>>>(h->B, par, w, lam, A, Bm, c, H); }
+    { Prof p(h, (cudaStream_t)stream, KC_OTHER); k_stage_derivs<<<nblk((long)h->B * NH, MPCB_EVAL_BLOCK), MPCB_EVAL_BLOCK, EVAL_SMEM_BYTES, (cudaStream_t)stream>>>(h->B, par, w, lam, A, Bm, c, H); }
     CK(cudaGetLastError());
     h->last_launches = 1;
     return 0;

@@ -52,17 +52,24 @@ struct ContCtx { const double* u; const double* par; const double* pxk; const do
 #ifndef MPCB_OCQ_NC
 #define MPCB_OCQ_NC 0
 #endif
+#ifndef MPCB_OCQ_NR
+#define MPCB_OCQ_NR 0
+#endif
 struct SysCont {
-    static constexpr int NS = NX + 1, NM = MPCB_CMX, NC = MPCB_OCQ_NC;
+    static constexpr int NS = NX + 1, NM = MPCB_CMX, NC = MPCB_OCQ_NC, NR = MPCB_OCQ_NR;
     typedef ContCtx Ctx;
-#if MPCB_OCQ_NC > 0
+#if MPCB_OCQ_NC + MPCB_OCQ_NR > 0
     MPCB_HDM void f_c(const double* x, const Ctx& c, double, double* o, double* cache) { ocq_f_c(x, c.u, c.par, c.pxk, c.pyk, o, cache); }
-    MPCB_HDM void f_vjp_c(const double* x, const Ctx& c, double, const double* nu, const double* cache, double* o) {
-        ocq_f_vjp_c(x, c.u, c.par, c.pxk, c.pyk, nu, cache, o);
+    MPCB_HDM void f_rc(const double* x, const Ctx& c, double, const double* cache, double* o, double* rc) {
+        ocq_f_rc(x, c.u, c.par, c.pxk, c.pyk, cache, o, rc);
+    }
+    MPCB_HDM void f_rcp(const double* x, const Ctx& c, double, const double* cache, double* rc) { ocq_f_rcp(x, c.u, c.par, c.pxk, c.pyk, cache, rc); }
+    MPCB_HDM void f_vjp_c(const double* x, const Ctx& c, double, const double* nu, const double* cache, const double* rc, double* o) {
+        ocq_f_vjp_c(x, c.u, c.par, c.pxk, c.pyk, nu, cache, rc, o);
     }
     MPCB_HDM void f_sh_c(const double* x, const Ctx& c, double, const double* S, const double* nu, const double* cache,
-                         double* o, double* K, double* Hc) {
-        ocq_f_sh_c(x, c.u, c.par, c.pxk, c.pyk, S, nu, cache, o, K, Hc);
+                         const double* rc, double* o, double* K, double* Hc) {
+        ocq_f_sh_c(x, c.u, c.par, c.pxk, c.pyk, S, nu, cache, rc, o, K, Hc);
     }
 #endif
     MPCB_HDM void f(const double* x, const Ctx& c, double, double* o) { ocq_f(x, c.u, c.par, c.pxk, c.pyk, o); }
@@ -275,13 +282,23 @@ MPCB_HD void bound_terms(double v, double lo, double hi, double zl, double zu, d
                          double* zsum, double* nb, double* pmin, double* pmax, double* prod) {
     *iL = *iU = *zL = *zU = *qL = *qU = 0.0;
     if (!active) return;
-    if (fin(lo)) { const double d = v - rlo(lo, rf); const double id = 1.0 / d; *iL = id; *zL = zl; *qL = id / zl; *sig += zl * id;
+    if (fin(lo)) { const double d = v - rlo(lo, rf); const double id = MPCB_RCP(d); *iL = id; *zL = zl; *qL = id * MPCB_RCP(zl); *sig += zl * id;
                    *zsum += zl; *nb += 1.0; *pmin = fmin(*pmin, d * zl); *pmax = fmax(*pmax, d * zl); *prod *= d; }
-    if (fin(hi)) { const double d = rhi(hi, rf) - v; const double id = 1.0 / d; *iU = id; *zU = zu; *qU = id / zu; *sig += zu * id;
+    if (fin(hi)) { const double d = rhi(hi, rf) - v; const double id = MPCB_RCP(d); *iU = id; *zU = zu; *qU = id * MPCB_RCP(zu); *sig += zu * id;
                    *zsum += zu; *nb += 1.0; *pmin = fmin(*pmin, d * zu); *pmax = fmax(*pmax, d * zu); *prod *= d; }
 }
 
-MPCB_HD void ocp_eval_stage(OcpInst& I, const OcpShared& S, int k) {
+// sub-step records of the RK4 sweeps: the model's, or the cost-augmented system's for ContForm problems
+#if MPCB_CONTFORM
+#define EVAL_RK_DOUBLES (RkSize<SysCont>::TOTAL)
+#elif MPCB_DYN_RK4
+#define EVAL_RK_DOUBLES (RkSize<SysModel>::TOTAL)
+#else
+#define EVAL_RK_DOUBLES 0
+#endif
+
+template <bool EXT = false>
+MPCB_HD void ocp_eval_stage(OcpInst& I, const OcpShared& S, int k, RkBuf rb = RkBuf{nullptr, 1}) {
     const double* w = I.w;
     const double rf = S.o.bound_relax;
     double z[NXA], u[NU], lam[NXA], d[ND + 1], px[NPX + 1], py[NPY + 1], t0;
@@ -302,7 +319,12 @@ MPCB_HD void ocp_eval_stage(OcpInst& I, const OcpShared& S, int k) {
         xt[NX] = 0.0; lt[NX] = 1.0;
 #pragma unroll
         for (int i = 0; i < NZS * (NZS + 1) / 2; ++i) Ht[i] = 0.0;
-        rk4_full_t<SysCont>(xt, cc, t0, lt, xe, S, Ht);
+        if constexpr (EXT) {
+            rk4_full_t<SysCont>(xt, cc, t0, lt, xe, S, Ht, rb);
+        } else {
+            double lbuf[RkSize<SysCont>::TOTAL];
+            rk4_full_t<SysCont>(xt, cc, t0, lt, xe, S, Ht, RkBuf{lbuf, 1});
+        }
         l = xe[NX];
 #pragma unroll
         for (int j = 0; j < NZ; ++j) {
@@ -317,13 +339,13 @@ MPCB_HD void ocp_eval_stage(OcpInst& I, const OcpShared& S, int k) {
         for (int i = 0; i < NX; ++i) xn[i] = xe[i];
     }
 #elif NAUG == 0
-    dyn_full(z, u, d, px, t0, lam, xn, A, Bm, Hp);
+    dyn_full<EXT>(z, u, d, px, t0, lam, xn, A, Bm, Hp, rb);
 #else
     {   // model part by the RK4 sweeps, then embedded into the augmented stage:  z+ = [Fx(x,u); u]
         double xm[NX], Am[NX * NX], Bmm[NX * NU], Hm[NZP];
 #pragma unroll
         for (int i = 0; i < NZP; ++i) Hm[i] = 0.0;
-        dyn_full(z, u, d, px, t0, lam, xm, Am, Bmm, Hm);
+        dyn_full<EXT>(z, u, d, px, t0, lam, xm, Am, Bmm, Hm, rb);
 #pragma unroll
         for (int i = 0; i < NXA * NXA; ++i) A[i] = 0.0;
 #pragma unroll

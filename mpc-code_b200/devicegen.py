@@ -31,22 +31,30 @@ def _depends_on(expr: SX, var: SX) -> bool:
     return any(s.uid in ids for s in S.symbols_of(expr.elements()))
 
 
-def _cached_variants(prefix: str, base, f, vjp_in, vjp_out, sh_in, sh_out, tainted) -> List[CFunction]:
-    """``<prefix>f_c`` (value + stage cache), ``f_vjp_c`` / ``f_sh_c`` (take the cache): the three RK4 sweeps visit
-    the same stage points, so transcendentals and reciprocals of the right-hand side are evaluated once per point
-    instead of three times.  Empty when the right-hand side has nothing expensive to share."""
+def _cached_variants(prefix: str, base, f, vjp_in, vjp_out, sh_in, sh_out, tainted):
+    """Variants of the right-hand side functions that share expensive sub-expressions between the RK4 sweeps, which
+    visit the same stage points three times.  Two levels:
+
+    * ``cache`` - transcendental values (exp, tanh, ...): computed once per stage point in sweep A (``f_c``), STORED
+      in the sweeps' record, read by everything evaluated at that point later.
+    * ``rc``    - reciprocals of the model's non-constant denominators (an FP64 reciprocal is ~12 instructions):
+      recomputed once per stage point per sweep (``f_rc`` / ``f_rcp``) and kept in REGISTERS for the adjoint and
+      second-order products at that point.  Not stored: in round 1 storing them doubled the kernel's DRAM traffic.
+
+    Returns ``(functions, NC, NR)``; empty when the right-hand side has nothing to share."""
     consumers = [[e for _, o in vjp_out for e in SX(o).elements()], [e for _, o in sh_out for e in SX(o).elements()]]
-    # Measured on B200 (Ex_NMPC, profiles/r01_v11_*): caching exp AND the two reciprocals (3 doubles per stage point)
-    # cuts the kernel's instructions by 28 % but doubles its DRAM traffic (the per-thread stage buffer grows from 960 to
-    # 1 920 B and no longer stays in L2): 0.317 -> 0.298 ms per launch.  Caching the transcendental only (1 280 B):
-    # 0.277 ms.  So reciprocals (~10 instructions) are recomputed; MPCB_CACHE_RECIPS=1 restores the larger cache.
-    import os
-    entries = expensive_entries(consumers, tainted, recips=os.environ.get("MPCB_CACHE_RECIPS", "0") == "1")
+    entries = expensive_entries(consumers, tainted, recips=True)
     if not entries:
-        return []
-    return [CFunction(prefix + "f_c", base, [("xdot", f), ("cache", cache_expressions(entries))]),
-            CFunction(prefix + "f_vjp_c", base + vjp_in, vjp_out, cache_in=("cache", entries)),
-            CFunction(prefix + "f_sh_c", base + sh_in, sh_out, cache_in=("cache", entries))]
+        return [], 0, 0
+    nodes = [e for e in entries if e[0] == "node"]
+    recips = [e for e in entries if e[0] == "recip"]
+    cache, rc = ("cache", nodes), ("rc", recips)
+    fns = [CFunction(prefix + "f_c", base, [("xdot", f), ("cache", cache_expressions(nodes))]),
+           CFunction(prefix + "f_rc", base, [("xdot", f), ("rc", cache_expressions(recips))], cache_in=[cache]),
+           CFunction(prefix + "f_rcp", base, [("rc", cache_expressions(recips))], cache_in=[cache]),
+           CFunction(prefix + "f_vjp_c", base + vjp_in, vjp_out, cache_in=[cache, rc]),
+           CFunction(prefix + "f_sh_c", base + sh_in, sh_out, cache_in=[cache, rc])]
+    return fns, len(nodes), len(recips)
 
 
 def _rhs_functions(prefix: str, rhs: Function, nx: int, nu: int, nd: int, npx: int, nxi: int) -> List[CFunction]:
@@ -71,8 +79,10 @@ def _rhs_functions(prefix: str, rhs: Function, nx: int, nu: int, nd: int, npx: i
     Hc = mtimes(dZ.T, mtimes(Hf, dZ))
     sh_out = [("xdot", f), ("K", K), ("Hc", tril_pack(Hc))]
     fns.append(CFunction(prefix + "f_sh", base + [("S", Sxu), ("nu", nu_adj)], sh_out))
-    fns += _cached_variants(prefix, base, f, [("nu", nu_adj)], [("fxTnu", gradient(nuf, x))],
-                            [("S", Sxu), ("nu", nu_adj)], sh_out, list(nu_adj.elements()) + list(Sxu.elements()))
+    cached, nc, nr = _cached_variants(prefix, base, f, [("nu", nu_adj)], [("fxTnu", gradient(nuf, x))],
+                                      [("S", Sxu), ("nu", nu_adj)], sh_out, list(nu_adj.elements()) + list(Sxu.elements()))
+    fns += cached
+    _rhs_functions.last_cache = (nc, nr)
     # sensitivities with respect to xi = (x0[, d]) for the estimator
     Sxi = SX.sym("S", nx, nxi)
     Kd = mtimes(fx, Sxi)
@@ -116,7 +126,7 @@ def generate_header(prob, ss_spec, ocp_spec, opts: Optional[Dict] = None) -> Dic
         D["MPCB_DYN_RK4"] = 1
         D["MPCB_MX"] = int(prob.Fx_model.meta["substeps"])
         fns += _rhs_functions("mdl_", prob.Fx_model.meta["rhs"], nx, nu, nd, npx, prob.nxi)
-        D["MPCB_MDL_NC"] = next((f.outputs[1][1].numel() for f in fns if f.name == "mdl_f_c"), 0)
+        D["MPCB_MDL_NC"], D["MPCB_MDL_NR"] = _rhs_functions.last_cache
         d_, px_ = SX.sym("d", nd), SX.sym("px", npx)
         post = prob.Fx_model.meta["post"](d_, px_)
         fns.append(CFunction("mdl_post", [("d", d_), ("px", px_)], [("post", post), ("Jd", jacobian(post, d_))]))
@@ -197,10 +207,10 @@ def generate_header(prob, ss_spec, ocp_spec, opts: Optional[Dict] = None) -> Dic
             fns.append(CFunction("ocq_f", base_q, [("xdot", rhs_t)]))
             fns.append(CFunction("ocq_f_vjp", base_q + [("nu", nu_adj)], [("fxTnu", gradient(nuf, xt))]))
             fns.append(CFunction("ocq_f_sh", base_q + [("S", St), ("nu", nu_adj)], sh_out))
-            cached = _cached_variants("ocq_", base_q, rhs_t, [("nu", nu_adj)], [("fxTnu", gradient(nuf, xt))],
-                                      [("S", St), ("nu", nu_adj)], sh_out, list(nu_adj.elements()) + list(St.elements()))
+            cached, nc, nr = _cached_variants("ocq_", base_q, rhs_t, [("nu", nu_adj)], [("fxTnu", gradient(nuf, xt))],
+                                              [("S", St), ("nu", nu_adj)], sh_out, list(nu_adj.elements()) + list(St.elements()))
             fns += cached
-            D["MPCB_OCQ_NC"] = cached[0].outputs[1][1].numel() if cached else 0
+            D["MPCB_OCQ_NC"], D["MPCB_OCQ_NR"] = nc, nr
             stage_cost = SX(0.0)
         else:
             D.update(MPCB_CONTFORM=0, MPCB_CMX=1)

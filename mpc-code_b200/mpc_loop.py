@@ -71,8 +71,9 @@ class BatchedMpc:
             self.h.set_const("K_est", est["K"])
         else:
             self.h.set_const("Q_kf", est["Q"]); self.h.set_const("R_kf", est["R"])
-        if est["dmin"] is not None and p.nd:
-            self.h.set_const("dmin", est["dmin"]); self.h.set_const("dmax", est["dmax"])
+        if (est["dmin"] is not None or est["dmax"] is not None) and p.nd:      # one-sided bounds: the other side is open
+            self.h.set_const("dmin", est["dmin"] if est["dmin"] is not None else np.full(p.nd, -np.inf))
+            self.h.set_const("dmax", est["dmax"] if est["dmax"] is not None else np.full(p.nd, np.inf))
         self.reset()
 
     # -- state -----------------------------------------------------------------
@@ -208,7 +209,7 @@ class BatchedMpc:
                 t.cuda.synchronize(dev); out["TIME_DYN"] = time.time() - t0
             st = self.solver.stats()["status"]
             self.dyn_status = st
-            okd = (st != INFEASIBLE).unsqueeze(1)                                                           # :786-805
+            okd = ((st != INFEASIBLE) & (st != -13)).unsqueeze(1)            # :786-805; a NaN iterate (-13) is never adopted
             w_new = sol["x"]
             self.w_opt = w_new if self.w_opt is None else t.where(okd, w_new, self.w_opt)
             x_pred = h.model_step(self.xhat_k, self.u_k, self.dhat_k, tt, p_x_k)
@@ -233,7 +234,10 @@ class BatchedMpc:
 
     # -- the same step through the fused C entry point (mpcb_step): no host glue between the solves ----------
     def fused_reset(self):
-        """Hand the current loop state to the device-resident loop of `mpcb_step`."""
+        """Hand the current loop state to the device-resident loop of `mpcb_step`.  Only at the start of a run: the
+        device loop keeps more state than is handed over here (previous targets, warm start, the first-step flag)."""
+        if self.ksim > 0:
+            raise RuntimeError("fused_reset after %d step() calls: switch between step() and step_fused() only after reset()" % self.ksim)
         self.solver_ss._push_bounds(None, None, None, None)      # w_lb/w_ub/g_lb/g_ub of the builders -> device constants
         self.solver._push_bounds(None, None, None, None)
         self.h.loop_reset(self.xhat_k, self.u_k, self.dhat_k if self.prob.nd else None, self.P_k)
@@ -287,6 +291,8 @@ class BatchedMpc:
         """Run ``Nsim`` steps and stack the per-step records into ``[Nsim, B, n]`` tensors (``MPC_code.py:877-895``)."""
         t = self.torch
         Nsim = self.prob.Nsim if Nsim is None else Nsim
+        if fused and state_noise is not None:
+            raise NotImplementedError("state noise is not applied by the fused step: use fused=False")
         rec: Dict[str, list] = {}
         for k in range(Nsim):
             if fused:

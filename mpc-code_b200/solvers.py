@@ -372,7 +372,20 @@ class BatchedNlpSolver:
     def stats(self):
         if self._last is None:
             raise RuntimeError("stats() before the first solve")
-        st, it = self._last
-        codes = st.cpu().numpy()
-        return {"return_status": [STATUS_NAMES.get(int(c), "Internal_Error") for c in codes],
-                "status": st, "iter_count": it, "success": bool(np.all((codes == 0) | (codes == 1)))}
+        return _Stats(*self._last)
+
+
+class _Stats(dict):
+    """``solver.stats()``: ``status`` / ``iter_count`` are device tensors; ``return_status`` (IPOPT's strings, one per
+    instance) and ``success`` need the codes on the host and are only fetched when asked for (a blocking copy)."""
+
+    def __init__(self, status, iters):
+        super().__init__(status=status, iter_count=iters)
+
+    def __missing__(self, key):
+        if key not in ("return_status", "success"):
+            raise KeyError(key)
+        codes = self["status"].cpu().numpy()
+        self["return_status"] = [STATUS_NAMES.get(int(c), "Internal_Error") for c in codes]
+        self["success"] = bool(np.all((codes == 0) | (codes == 1)))
+        return dict.__getitem__(self, key)

@@ -43,7 +43,8 @@ class OracleLoop:
         p_yp = np.asarray(ns["def_pyp"](t_k)[0], dtype=float).ravel() if "def_pyp" in ns else np.zeros(p.npyp)
         return p_xk, p_yk, p_xmp, p_ymp, p_xp, p_yp
 
-    def run(self, Nsim=None, x0_p=None, x0_m=None, noise=None, state_noise=None):
+    def run(self, Nsim=None, x0_p=None, x0_m=None, noise=None, state_noise=None, on_step=None):
+        """``on_step(k)`` (optional) is called at the start of every step - bench.py's CPU leg uses it for time stamps."""
         p, c = self.prob, self.c
         nx, nu, ny, nd, N, h = p.nx, p.nu, p.ny, p.nd, p.N, p.h
         nxu = nx + nu
@@ -65,6 +66,8 @@ class OracleLoop:
         last_dyn_status = 0
         xs_k = us_k = None
         for ksim in range(Nsim):
+            if on_step is not None:
+                on_step(ksim)
             t_k = ksim * h
             p_xk, p_yk, p_xmp, p_ymp, p_xp, p_yp = self._params(t_k)
             p_x_k, p_y_k = p_xk[:, 0], p_yk[:, 0]

@@ -164,3 +164,13 @@ def enmpc():
 @pytest.fixture(scope="session")
 def lmpc_nlplant():
     return _bundle("lmpc_nlplant")
+
+
+@pytest.fixture(scope="session")
+def nmpc_dis():
+    return _bundle("nmpc_dis")
+
+
+@pytest.fixture(scope="session")
+def lmpcxp_nlplant():
+    return _bundle("lmpcxp_nlplant")

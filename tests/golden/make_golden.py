@@ -5,6 +5,7 @@
 * ``kat.json``  - known-answer facts read from the reference's own example files:
   KAT1 steady state of Ex_NMPC.py, KAT2 the printed linearisation in Ex_LMPC_nlplant.py:85-91,
   KAT3 closed-form targets derived from Ex_NMPC.py:129-148,217-219,241-242.
+* ``ref_examples_oracle.npz`` - oracle closed loops of the unmodified Ex_NMPC_dis.py and Ex_LMPCxp_nlplant.py.
 * ``nmpc_oracle.npz`` - outputs of the CPU oracle on the UNMODIFIED /root/reference/Ex_NMPC.py
   (loaded through the casadi stand-in): OCP and target solutions, EKF updates, a short closed loop.
 """
@@ -56,7 +57,26 @@ def make_synthetic(names):
     np.savez_compressed(syn_path, **syn)
 
 
+def make_reference_examples():
+    """Oracle closed loops of the UNMODIFIED reference files that the BASELINE configurations do not cover: the discrete
+    model with `if_else` clamps, Delta-u bounds and a user terminal cost (Ex_NMPC_dis.py:75-77,120-125), and nx != nxp
+    (Ex_LMPCxp_nlplant.py:98).  The GPU tests run the repo's own restatements of these files (examples/) against them."""
+    out = {}
+    for fname, tag, Ns in (("Ex_NMPC_dis.py", "nmpc_dis", 16), ("Ex_LMPCxp_nlplant.py", "lmpcxp_nlplant", 110)):
+        prob = build_problem(load_example(os.path.join(REF, fname)))
+        ss, ocp = make_specs(prob)
+        mod = cmodel.build("ref_" + tag, prob, ocp, ss)
+        rec = OracleLoop(prob, ss, ocp, mod).run(Nsim=Ns)
+        print(fname, "status", rec["STATUS_DYN"], "iters", rec["ITER_DYN"])
+        for key in ("U", "X_HAT", "D_HAT", "XS", "US", "Xp", "Yp", "F_DYN", "ITER_DYN", "STATUS_DYN", "STATUS_SS"):
+            out["%s_%s" % (tag, key)] = rec[key]
+    np.savez_compressed(os.path.join(HERE, "ref_examples_oracle.npz"), **out)
+
+
 def main():
+    if "--only-examples" in sys.argv:                             # python make_golden.py --only-examples
+        make_reference_examples()
+        return
     only = [a for a in sys.argv if a.startswith("--only-synthetic=")]
     if only:                                                      # python make_golden.py --only-synthetic=syn_12_4_20
         make_synthetic(tuple(only[0].split("=", 1)[1].split(",")))
@@ -155,6 +175,7 @@ def main():
     syn_args = [a for a in sys.argv if a.startswith("--synthetic")]       # --synthetic  or  --synthetic=syn_12_4_20,...
     if syn_args:
         make_synthetic(tuple(syn_args[0].split("=", 1)[1].split(",")) if "=" in syn_args[0] else ("syn_8_3_50",))
+    make_reference_examples()
     print("wrote fixtures")
 
 

@@ -45,12 +45,17 @@ def launches(path):
         print("%-64s %8d %14.1f %10.1f %8.4f" % (k[:64], v[0], v[1], v[1] / v[0], v[1] / tot))
 
 
-def report(path):
+def report(path, longest_only=False):
     out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
     print("# ncu --set full --clock-control none : %s" % path)
-    for r in rows[2:]:
+    body = rows[2:]
+    if longest_only:                       # the launch with every instance active (first tick of a step)
+        i_t = hdr.index("gpu__time_duration.sum")
+        body = [max(body, key=lambda r: float(r[i_t].replace(",", "")))]
+        print("# longest of %d captured launches" % (len(rows) - 2))
+    for r in body:
         name = r[hdr.index("Kernel Name")]
         print("\n== %s" % name)
         for key in KEYS:
@@ -60,4 +65,7 @@ def report(path):
 
 
 if __name__ == "__main__":
-    {"launches": launches, "report": report}[sys.argv[1]](sys.argv[2])
+    if sys.argv[1] == "longest":
+        report(sys.argv[2], longest_only=True)
+    else:
+        {"launches": launches, "report": report}[sys.argv[1]](sys.argv[2])

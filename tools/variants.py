@@ -11,11 +11,11 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 VARIANTS = {
-    "default": "",
-    "scalar_record_stores": "-DMPCB_VEC_REC=0",
-    "eval128x2": "-DMPCB_EVAL_MINBLOCKS=2",
-    "kkt_warps2": "-DKKT_WARPS=2",
-    "kkt_warps8": "-DKKT_WARPS=8",
+    "eval128x3_r168": "",
+    "eval128x2_r254": "-DMPCB_EVAL_MINBLOCKS=2",
+    "eval64x5_r200": "-DMPCB_EVAL_BLOCK=64 -DMPCB_EVAL_MINBLOCKS=5 -DMPCB_EVAL_MAXNREG=200",
+    "eval32x9_r224": "-DMPCB_EVAL_BLOCK=32 -DMPCB_EVAL_MINBLOCKS=9 -DMPCB_EVAL_MAXNREG=224",
+    "eval32x11_r184": "-DMPCB_EVAL_BLOCK=32 -DMPCB_EVAL_MINBLOCKS=11 -DMPCB_EVAL_MAXNREG=184",
 }
 
 if __name__ == "__main__":
