@@ -26,7 +26,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 BATCH_PER_GPU = 4096
-DEFAULT_GROUPS = 8         # instance groups of the fused step (mpcb_set_groups); MPCB_GROUPS overrides
+DEFAULT_GROUPS = 2         # instance groups of the fused step (mpcb_set_groups); MPCB_GROUPS overrides.  Measured with the
+#                            device-driven solve (profiles/r02_groups_sweep*.txt): 1 group 687k, 2 groups 697k, 4 groups 584k, 8 groups 505k steps/s
 SEED_X0, SEED_NOISE = 20240419, 7
 X0_SCALE = np.array([0.02, 0.002, 0.02])
 METRIC = "batched MPC steps/sec (Ex_NMPC CSTR, N=50, FP64)"
@@ -289,10 +290,9 @@ def run_gpu(args):
     ys = torch.empty(total, B, prob.ny, device=dev, dtype=torch.float64)
     us = torch.empty(total, B, prob.nu, device=dev, dtype=torch.float64)
     st_dyn = torch.empty(K, B, device=dev, dtype=torch.int32); it_dyn = torch.empty_like(st_dyn); st_ss = torch.empty_like(st_dyn)
-    # one host thread per group spins on its stream: one core per thread and one spare per rank, never more than
-    # DEFAULT_GROUPS (measured at 8 ranks on 32 cores: 2 groups 4.73 M, 3 groups 4.82 M, 4 groups 4.55 M steps/s)
-    cores_here = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    groups = int(os.environ.get("MPCB_GROUPS", max(1, min(DEFAULT_GROUPS, cores_here // world - 1))))
+    # instance groups: sub-batches queued on their own streams by this one thread (no polling threads since round 2: the
+    # solve is a device-driven CUDA graph), so the number of groups no longer depends on the host's core count
+    groups = int(os.environ.get("MPCB_GROUPS", DEFAULT_GROUPS))
     ctl.h.set_groups(groups)
     for k in range(W):
         o = ctl.step_fused(noise_dev[k]); ys[k].copy_(o["Yp"]); us[k].copy_(o["U"])

@@ -9,9 +9,10 @@
  * Conventions
  *  - every data pointer is DEVICE memory (float64 / int32), instance-major: element j of
  *    instance i lives at ptr[i * len + j]; the caller owns all buffers;
- *  - `stream` is a cudaStream_t passed as void*; kernels are enqueued on it.  mpcb_ocp and
- *    mpcb_target poll a device-side "instances still iterating" counter and therefore
- *    synchronise that stream before returning; the other calls are asynchronous;
+ *  - `stream` is a cudaStream_t passed as void*; kernels are enqueued on it and EVERY call is asynchronous: outputs
+ *    are complete when the stream reaches that point.  The iterative solves (mpcb_ocp, mpcb_step) are device driven -
+ *    one CUDA graph whose WHILE node repeats the solver tick until no instance iterates - so the host never waits on
+ *    them.  (With profiling on, see mpcb_set_profiling, they run a host-polled schedule and return when done.);
  *  - return value 0 = OK, < 0 = error (text via mpcb_last_error); a handle is bound to the
  *    device that was current at mpcb_create and is not thread-safe;
  *  - problem sizes and the user's model are compiled in (generated header); mpcb_get_dims
@@ -134,11 +135,11 @@ int  mpcb_step(mpcb_handle_t h, int est_type, const double* y_meas, const double
                double* f_dyn, int* status_dyn, int* iters_dyn, int* status_ss, void* stream);
 int  mpcb_loop_get(mpcb_handle_t h, double* xi, double* P, double* u, void* stream);
 
-/* Instance groups of the fused step: mpcb_step cuts the batch into n contiguous groups, each driven by its own host
- * thread and CUDA stream, so that the latency-bound phases of one group (Riccati sweep, target solve, the tail of
- * iterations in which few instances are still active) overlap the evaluation kernels of another.  Results do not
- * change (instances are independent - the reference solves them one after another, MPC_code.py:485).  With n > 1
- * mpcb_step returns with all outputs complete.  Default 1. */
+/* Instance groups of the fused step: mpcb_step cuts the batch into n contiguous groups, each queued on its own CUDA
+ * stream (all launches made by the calling thread), so that the latency-bound phases of one group (Riccati sweep,
+ * target solve, the tail of iterations in which few instances are still active) overlap the evaluation kernels of
+ * another.  Results do not change (instances are independent - the reference solves them one after another,
+ * MPC_code.py:485).  The caller's stream is made to wait for all groups.  Default 1. */
 int  mpcb_set_groups(mpcb_handle_t h, int n);
 
 /* Profiling.  With profiling on, every kernel launch is bracketed by CUDA events on its stream and the
@@ -155,9 +156,13 @@ int  mpcb_get_profile(mpcb_handle_t h, double* kernel_ms /*[8]*/, long* kernel_l
  * the measured denominator for FP64 roofline fractions (MEASURED_PEAKS.json has no FP64 entry). */
 int  mpcb_dfma_peak(int iters, double* tflops);
 
-/* Counters of the last mpcb_ocp / mpcb_target call: kernel launches, solver ticks. */
+/* Counters.  mpcb_last_ticks: solver ticks of the last OCP solve (largest over the groups); mpcb_total_launches:
+ * kernel launches made through the handle since mpcb_create, the ticks of the device-driven solves included (4 launches
+ * each).  Both wait for the handle's streams - the tick counts live on the device.  mpcb_last_launches: launches of the
+ * last host-polled call, -1 after a device-driven one. */
 int  mpcb_last_launches(mpcb_handle_t h);
 int  mpcb_last_ticks(mpcb_handle_t h);
+long mpcb_total_launches(mpcb_handle_t h);
 
 #ifdef __cplusplus
 }

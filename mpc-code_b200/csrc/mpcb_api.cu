@@ -5,10 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <string.h>
-#include <condition_variable>
-#include <mutex>
+#include <stdlib.h>
 #include <string>
-#include <thread>
 #include <utility>
 #include <vector>
 #include "mpcb.h"
@@ -121,6 +119,7 @@ __global__ void __launch_bounds__(128) k_ocp_trial(OcpArgs a) {
     ocp_trial_stage(I, a.S, k);
 }
 
+// n_active != null: count the instances that are not done after this tick
 __global__ void __launch_bounds__(32 * KKT_WARPS) k_ocp_accept(OcpArgs a, int* n_active) {
     const int inst = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (inst >= a.B) return;
@@ -128,7 +127,18 @@ __global__ void __launch_bounds__(32 * KKT_WARPS) k_ocp_accept(OcpArgs a, int* n
         OcpInst I = ocp_view(a, inst);
         ocp_accept(I, a.S);
     }
-    if ((threadIdx.x & 31) == 0 && a.st[inst].state != ST_DONE) atomicAdd(n_active, 1);
+    if (n_active && (threadIdx.x & 31) == 0 && a.st[inst].state != ST_DONE) atomicAdd(n_active, 1);
+}
+
+// Loop condition of the device-driven solve (body of the CUDA-graph WHILE node, after k_ocp_accept): another tick while
+// some instance still iterates.  ctr = {instances not done (reset here), ticks of this solve, ticks since creation}.
+// `ticks` = number of ticks run since the previous call of this kernel.
+__global__ void k_ocp_cond(cudaGraphConditionalHandle handle, int* n_active, unsigned long long* ctr, int max_ticks, int ticks) {
+    const int active = *n_active;
+    *n_active = 0;
+    const unsigned long long t = (ctr[0] += (unsigned long long)ticks);
+    ctr[1] += (unsigned long long)ticks;
+    cudaGraphSetConditional(handle, (active > 0 && t < (unsigned long long)max_ticks) ? 1u : 0u);
 }
 
 __global__ void k_ocp_output(OcpArgs a, double* f, int* status, int* iters) {
@@ -359,6 +369,13 @@ struct mpcb_ctx {
     InstState* st;
     int* n_active; int* h_active;
     int have_dbounds, last_launches, last_ticks;
+    // device-driven solve: a CUDA graph [init -> WHILE {eval, kkt, trial, accept, cond} -> output], rebuilt when the
+    // caller's buffers or the options change; tick counters on the device; launches made from the host so far
+    cudaGraph_t og_graph; cudaGraphExec_t og_exec;
+    const void* og_key[5]; mpcb_opts_t og_opts; int og_valid;
+    double* stage_mem; int* stage_imem;      // staging copies of par | w | f and status | iters for callers whose buffers move
+    unsigned long long* tick_ctr;            // device: {ticks of the last solve, ticks since creation}
+    long host_launches; int host_loop; cudaStream_t last_stream;
     // loop state of the fused step (mpcb_loop_reset / mpcb_step)
     double* loop_mem; int* loop_imem; int loop_first;
 #if MPCB_HAS_OCP && MPCB_HAS_TARGET
@@ -371,22 +388,13 @@ struct mpcb_ctx {
     unsigned long long eval_instances, trial_instances;
     std::vector<cudaEvent_t> ev_pool;
     std::vector<std::pair<int, int>> ev_pending;   // (kernel class, index of start event; stop = +1)
-    // instance groups of the fused step (mpcb_set_groups): sub-batches driven by their own host thread and stream
+    // instance groups of the fused step (mpcb_set_groups): sub-batches queued on their own streams
     int ngroups;
     std::vector<struct StepGroup*> groups;
     cudaEvent_t ev_in;
 };
 
-struct StepArgs {
-    int est_type; const double *y_meas, *t, *sp, *px, *py;
-    double *u_out, *xhat_out, *dhat_out, *xs_out, *us_out, *f_dyn; int *status_dyn, *iters_dyn, *status_ss;
-};
-struct StepGroup {
-    mpcb_ctx* c; int b0, nb; cudaStream_t s;
-    std::thread th; std::mutex m; std::condition_variable cv;
-    long job = 0, done = 0; bool quit = false; int rc = 0;
-    StepArgs a;
-};
+struct StepGroup { mpcb_ctx* c; int b0, nb; cudaStream_t s; cudaEvent_t done; };
 
 static IpmOpts to_ipm(const mpcb_opts_t& o) {
     IpmOpts r;
@@ -468,6 +476,9 @@ long mpcb_model_flops(const char* name) {
 int mpcb_create(int batch, const mpcb_opts_t* oss, const mpcb_opts_t* odyn, mpcb_handle_t* out) {
     mpcb_ctx* h = new mpcb_ctx();
     h->B = batch; h->have_dbounds = 0; h->last_launches = 0; h->last_ticks = 0;
+    h->og_graph = nullptr; h->og_exec = nullptr; h->og_valid = 0; h->tick_ctr = nullptr; h->host_launches = 0; h->last_stream = nullptr;
+    h->stage_mem = nullptr; h->stage_imem = nullptr;
+    { const char* e = getenv("MPCB_HOST_LOOP"); h->host_loop = (e && e[0] == '1') ? 1 : 0; }
     mpcb_default_opts(&h->opts_ss); mpcb_default_opts(&h->opts_dyn);
     if (oss) h->opts_ss = *oss;
     if (odyn) h->opts_dyn = *odyn;
@@ -496,7 +507,10 @@ int mpcb_create(int batch, const mpcb_opts_t* oss, const mpcb_opts_t* odyn, mpcb
     CK(cudaMemset(h->Qkf, 0, sizeof(double) * NXI * NXI)); CK(cudaMemset(h->Rkf, 0, sizeof(double) * NY * NY));
     CK(cudaMemset(h->Kest, 0, sizeof(double) * NXI * NY));
     CK(cudaMalloc(&h->n_active, sizeof(int)));
+    CK(cudaMemset(h->n_active, 0, sizeof(int)));
     CK(cudaMallocHost(&h->h_active, sizeof(int)));
+    CK(cudaMalloc(&h->tick_ctr, 2 * sizeof(unsigned long long)));
+    CK(cudaMemset(h->tick_ctr, 0, 2 * sizeof(unsigned long long)));
     CK(cudaMalloc(&h->counters, 2 * sizeof(unsigned long long)));
     CK(cudaMemset(h->counters, 0, 2 * sizeof(unsigned long long)));
     h->loop_mem = nullptr; h->loop_imem = nullptr; h->loop_first = 1;
@@ -508,9 +522,18 @@ int mpcb_create(int batch, const mpcb_opts_t* oss, const mpcb_opts_t* odyn, mpcb
 
 static void groups_teardown(mpcb_ctx* h);
 
+static void ocp_graph_drop(mpcb_ctx* h) {
+    if (h->og_exec) cudaGraphExecDestroy(h->og_exec);
+    if (h->og_graph) cudaGraphDestroy(h->og_graph);
+    h->og_exec = nullptr; h->og_graph = nullptr; h->og_valid = 0;
+}
+
 int mpcb_destroy(mpcb_handle_t h) {
     if (!h) return 0;
+    cudaDeviceSynchronize();
     groups_teardown(h);
+    ocp_graph_drop(h);
+    cudaFree(h->tick_ctr); cudaFree(h->stage_mem); cudaFree(h->stage_imem);
     if (h->ev_in) cudaEventDestroy(h->ev_in);
     cudaFree(h->ws); cudaFree(h->st); cudaFree(h->lbx); cudaFree(h->ubx); cudaFree(h->lbg); cudaFree(h->ubg);
     cudaFree(h->ss_lbx); cudaFree(h->ss_ubx); cudaFree(h->Qkf); cudaFree(h->Rkf); cudaFree(h->Kest);
@@ -561,15 +584,113 @@ int mpcb_set_const(mpcb_handle_t h, const char* name, const double* p, int n) {
 
 static inline int nblk(long n, int bs) { return (int)((n + bs - 1) / bs); }
 
-int mpcb_ocp(mpcb_handle_t h, const double* par, double* w, double* f, int* status, int* iters, void* stream) {
+static bool same_opts(const mpcb_opts_t& a, const mpcb_opts_t& b) {
+    return a.max_iter == b.max_iter && a.tol == b.tol && a.mu_init == b.mu_init && a.bound_relax_factor == b.bound_relax_factor &&
+           a.honor_original_bounds == b.honor_original_bounds && a.bound_push == b.bound_push &&
+           a.acceptable_tol == b.acceptable_tol && a.acceptable_iter == b.acceptable_iter;
+}
+
 #if MPCB_HAS_OCP
-    cudaStream_t s = (cudaStream_t)stream;
-    OcpArgs a;
-    a.B = h->B; a.par = par; a.w = w; a.ws = h->ws; a.st = h->st; a.counters = h->counters;
-    a.S.lbx = h->lbx; a.S.ubx = h->ubx; a.S.lbg = h->lbg; a.S.ubg = h->ubg; a.S.o = to_ipm(h->opts_dyn);
+// Build the device-driven solve as a CUDA graph:
+//   memset counters -> k_ocp_init -> U unrolled ticks -> k_ocp_cond -> WHILE { tick -> k_ocp_cond } -> k_ocp_output
+// with tick = k_ocp_eval -> k_ocp_kkt -> k_ocp_trial -> k_ocp_accept.  The loop condition is set on the device by k_ocp_cond
+// (cudaGraphSetConditional), so a whole solve - however many ticks its slowest instance needs - is ONE graph launch and the
+// host never waits on it (round 1 polled a device counter every two ticks, with one spinning host thread per group).
+// The first U ticks are plain kernel nodes: a node inside a WHILE body costs ~5 us of device-side scheduling that
+// serialises across streams (measured: profiles/r02_groups_sweep_graph.txt), a plain node ~1.5 us, and a tick whose
+// instances are all done is four kernels that exit at once.  U = MPCB_GRAPH_UNROLL (environment), default 10: a warm
+// closed-loop step of Ex_NMPC needs 11-13 ticks.
+static int add_tick(mpcb_ctx* h, cudaGraph_t g, cudaGraphNode_t* dep, int ndep, OcpArgs& a, int* n_active, cudaGraphNode_t* last) {
+    const int bs = 128;
+    const long nst = (long)h->B * NH;
+    cudaKernelNodeParams kp; memset(&kp, 0, sizeof(kp));
+    void* args1[] = {&a};
+    cudaGraphNode_t n_eval, n_kkt, n_trial;
+    kp.kernelParams = args1;
+    kp.func = (void*)k_ocp_eval; kp.gridDim = dim3(nblk(nst, MPCB_EVAL_BLOCK)); kp.blockDim = dim3(MPCB_EVAL_BLOCK);
+    kp.sharedMemBytes = (unsigned)EVAL_SMEM_BYTES;
+    CK(cudaGraphAddKernelNode(&n_eval, g, dep, ndep, &kp));
+    kp.sharedMemBytes = 0;
+    { dim3 gk(1), bk(1); auto set = [&](int gx, int bx) { gk = dim3(gx); bk = dim3(bx); }; set(KKT_GRID(h->B));
+      kp.func = (void*)k_ocp_kkt; kp.gridDim = gk; kp.blockDim = bk; }
+    CK(cudaGraphAddKernelNode(&n_kkt, g, &n_eval, 1, &kp));
+    kp.func = (void*)k_ocp_trial; kp.gridDim = dim3(nblk(nst, bs)); kp.blockDim = dim3(bs);
+    CK(cudaGraphAddKernelNode(&n_trial, g, &n_kkt, 1, &kp));
+    void* args2[] = {&a, &n_active};
+    kp.func = (void*)k_ocp_accept; kp.gridDim = dim3(nblk((long)h->B * 32, 32 * KKT_WARPS)); kp.blockDim = dim3(32 * KKT_WARPS);
+    kp.kernelParams = args2;
+    CK(cudaGraphAddKernelNode(last, g, &n_trial, 1, &kp));
+    return 0;
+}
+
+static int ocp_graph_build(mpcb_ctx* h, const OcpArgs& a_in, double* f, int* status, int* iters) {
+    ocp_graph_drop(h);
+    OcpArgs a = a_in;
+    const int bs = 128;
+    int max_ticks = (h->opts_dyn.max_iter + 2) * 8;
+    int unroll = 10;
+    { const char* e = getenv("MPCB_GRAPH_UNROLL"); if (e) unroll = atoi(e); }
+    if (unroll < 0) unroll = 0;
+    if (unroll > max_ticks) unroll = max_ticks;
+    CK(cudaGraphCreate(&h->og_graph, 0));
+    cudaGraph_t g = h->og_graph;
+    cudaGraphNode_t n_ms1, n_ms2, n_init, n_while, n_out, prev;
+    cudaMemsetParams ms; memset(&ms, 0, sizeof(ms));
+    ms.dst = h->n_active; ms.value = 0; ms.elementSize = 4; ms.width = 1; ms.height = 1; ms.pitch = 4;
+    CK(cudaGraphAddMemsetNode(&n_ms1, g, nullptr, 0, &ms));
+    ms.dst = h->tick_ctr; ms.width = 2;                                 // ticks of this solve (one 64-bit counter)
+    CK(cudaGraphAddMemsetNode(&n_ms2, g, nullptr, 0, &ms));
+    cudaKernelNodeParams kp; memset(&kp, 0, sizeof(kp));
+    void* args1[] = {&a};
+    kp.func = (void*)k_ocp_init; kp.gridDim = dim3(nblk((long)h->B * (NH + 1), bs)); kp.blockDim = dim3(bs); kp.kernelParams = args1;
+    cudaGraphNode_t dep0[] = {n_ms1, n_ms2};
+    CK(cudaGraphAddKernelNode(&n_init, g, dep0, 2, &kp));
+    prev = n_init;
+    int* n_active = h->n_active; int* no_count = nullptr;
+    for (int t = 0; t < unroll; ++t) {                                   // only the last unrolled tick counts the active instances
+        cudaGraphNode_t last;
+        int rc = add_tick(h, g, &prev, 1, a, (t == unroll - 1) ? n_active : no_count, &last);
+        if (rc) return rc;
+        prev = last;
+    }
+    cudaGraphConditionalHandle handle;
+    CK(cudaGraphConditionalHandleCreate(&handle, g, 1, cudaGraphCondAssignDefault));
+    unsigned long long* ctr = h->tick_ctr;
+    if (unroll > 0) {                                                    // condition for entering the WHILE tail
+        cudaGraphNode_t n_c0;
+        void* args3[] = {&handle, &n_active, &ctr, &max_ticks, &unroll};
+        kp.func = (void*)k_ocp_cond; kp.gridDim = dim3(1); kp.blockDim = dim3(1); kp.kernelParams = args3; kp.sharedMemBytes = 0;
+        CK(cudaGraphAddKernelNode(&n_c0, g, &prev, 1, &kp));
+        prev = n_c0;
+    }
+    cudaGraphNodeParams cp = { cudaGraphNodeTypeConditional };
+    cp.conditional.handle = handle; cp.conditional.type = cudaGraphCondTypeWhile; cp.conditional.size = 1;
+    CK(cudaGraphAddNode(&n_while, g, &prev, 1, &cp));
+    cudaGraph_t body = cp.conditional.phGraph_out[0];
+    {
+        cudaGraphNode_t last, n_cond;
+        int rc = add_tick(h, body, nullptr, 0, a, n_active, &last);
+        if (rc) return rc;
+        int one = 1;
+        void* args3[] = {&handle, &n_active, &ctr, &max_ticks, &one};
+        kp.func = (void*)k_ocp_cond; kp.gridDim = dim3(1); kp.blockDim = dim3(1); kp.kernelParams = args3; kp.sharedMemBytes = 0;
+        CK(cudaGraphAddKernelNode(&n_cond, body, &last, 1, &kp));
+    }
+    void* args4[] = {&a, &f, &status, &iters};
+    kp.func = (void*)k_ocp_output; kp.gridDim = dim3(nblk((long)h->B * (NH + 1), 128)); kp.blockDim = dim3(128); kp.kernelParams = args4;
+    CK(cudaGraphAddKernelNode(&n_out, g, &n_while, 1, &kp));
+    CK(cudaGraphInstantiate(&h->og_exec, g, 0));
+    h->og_key[0] = a.par; h->og_key[1] = a.w; h->og_key[2] = f; h->og_key[3] = status; h->og_key[4] = iters;
+    h->og_opts = h->opts_dyn; h->og_valid = 1;
+    return 0;
+}
+
+// host-polled variant of the same schedule: used with profiling on (event brackets around every launch) or MPCB_HOST_LOOP=1
+static int ocp_host_loop(mpcb_ctx* h, OcpArgs& a, double* f, int* status, int* iters, cudaStream_t s) {
     const int bs = 128;
     const long nst = (long)h->B * NH;
     int launches = 0, ticks = 0;
+    CK(cudaMemsetAsync(h->n_active, 0, sizeof(int), s));
     { Prof p(h, s, KC_OCP_INIT); k_ocp_init<<<nblk((long)h->B * (NH + 1), bs), bs, 0, s>>>(a); } launches++;
     // every instance needs at most max_iter+1 evaluations plus its line-search backtracks
     const int max_ticks = (h->opts_dyn.max_iter + 2) * 8;
@@ -588,6 +709,7 @@ int mpcb_ocp(mpcb_handle_t h, const double* par, double* w, double* f, int* stat
         prof_collect(h);
         if (*h->h_active == 0) break;
     }
+    CK(cudaMemsetAsync(h->n_active, 0, sizeof(int), s));
     { Prof p(h, s, KC_OTHER); k_ocp_output<<<nblk((long)h->B * (NH + 1), 128), 128, 0, s>>>(a, f, status, iters); } launches++;
     CK(cudaGetLastError());
     if (h->profile) {
@@ -597,7 +719,54 @@ int mpcb_ocp(mpcb_handle_t h, const double* par, double* w, double* f, int* stat
         prof_collect(h);
         h->eval_instances = cnt[0]; h->trial_instances = cnt[1];
     }
+    h->host_launches += launches;
     h->last_launches = launches; h->last_ticks = ticks;
+    return 0;
+}
+#endif
+
+// Asynchronous: the solve is queued on `stream` (one CUDA-graph launch) and the call returns; outputs are complete when
+// the stream reaches that point.  With profiling on it runs the host-polled schedule and returns after completion.
+int mpcb_ocp(mpcb_handle_t h, const double* par, double* w, double* f, int* status, int* iters, void* stream) {
+#if MPCB_HAS_OCP
+    cudaStream_t s = (cudaStream_t)stream;
+    OcpArgs a;
+    a.B = h->B; a.par = par; a.w = w; a.ws = h->ws; a.st = h->st; a.counters = h->counters;
+    a.S.lbx = h->lbx; a.S.ubx = h->ubx; a.S.lbg = h->lbg; a.S.ubg = h->ubg; a.S.o = to_ipm(h->opts_dyn);
+    h->last_stream = s;
+    if (h->profile || h->host_loop) return ocp_host_loop(h, a, f, status, iters, s);
+    // The graph holds its buffers' addresses.  A caller whose buffers stay put (the fused step; any caller that reuses its
+    // tensors) is served in place; one whose buffers move gets staging copies from its second call on, so that the graph
+    // is built once, not per call.
+    const void* key[5] = {par, w, f, status, iters};
+    const bool moved = h->og_valid && memcmp(key, h->og_key, sizeof(key)) != 0;
+    const size_t B = (size_t)h->B;
+    if (moved && !h->stage_mem) {
+        CK(cudaMalloc(&h->stage_mem, sizeof(double) * B * (NPAR + NW + 1)));
+        CK(cudaMalloc(&h->stage_imem, sizeof(int) * B * 2));
+    }
+    const bool staged = h->stage_mem != nullptr;
+    double* sp_ = h->stage_mem; double* sw_ = sp_ + B * NPAR; double* sf_ = sw_ + B * NW;
+    int* sst_ = h->stage_imem; int* sit_ = sst_ + B;
+    if (staged) {
+        CK(cudaMemcpyAsync(sp_, par, sizeof(double) * B * NPAR, cudaMemcpyDeviceToDevice, s));
+        CK(cudaMemcpyAsync(sw_, w, sizeof(double) * B * NW, cudaMemcpyDeviceToDevice, s));
+        a.par = sp_; a.w = sw_;
+        key[0] = sp_; key[1] = sw_; key[2] = sf_; key[3] = sst_; key[4] = sit_;
+    }
+    if (!h->og_valid || memcmp(key, h->og_key, sizeof(key)) || !same_opts(h->og_opts, h->opts_dyn)) {
+        int rc = staged ? ocp_graph_build(h, a, sf_, sst_, sit_) : ocp_graph_build(h, a, f, status, iters);
+        if (rc) return rc;
+    }
+    CK(cudaGraphLaunch(h->og_exec, s));
+    if (staged) {
+        CK(cudaMemcpyAsync(w, sw_, sizeof(double) * B * NW, cudaMemcpyDeviceToDevice, s));
+        CK(cudaMemcpyAsync(f, sf_, sizeof(double) * B, cudaMemcpyDeviceToDevice, s));
+        CK(cudaMemcpyAsync(status, sst_, sizeof(int) * B, cudaMemcpyDeviceToDevice, s));
+        CK(cudaMemcpyAsync(iters, sit_, sizeof(int) * B, cudaMemcpyDeviceToDevice, s));
+    }
+    h->host_launches += 2;                       // init + output; the ticks are counted on the device (4-5 launches each)
+    h->last_launches = -1; h->last_ticks = -1;   // known once the stream has run: see mpcb_last_ticks
     return 0;
 #else
     h->err = "library built without the OCP"; return -3;
@@ -607,6 +776,7 @@ int mpcb_ocp(mpcb_handle_t h, const double* par, double* w, double* f, int* stat
 int mpcb_stage_derivs(mpcb_handle_t h, const double* par, const double* w, const double* lam,
                       double* A, double* Bm, double* c, double* H, void* stream) {
 #if MPCB_HAS_OCP
+    h->host_launches += 1;
     { Prof p(h, (cudaStream_t)stream, KC_OTHER); k_stage_derivs<<<nblk((long)h->B * NH, MPCB_EVAL_BLOCK), MPCB_EVAL_BLOCK, EVAL_SMEM_BYTES, (cudaStream_t)stream>>>(h->B, par, w, lam, A, Bm, c, H); }
     CK(cudaGetLastError());
     h->last_launches = 1;
@@ -621,8 +791,8 @@ int mpcb_target(mpcb_handle_t h, const double* par_ss, double* wss, double* fss,
     TgtShared S; S.lbx = h->ss_lbx; S.ubx = h->ss_ubx; S.o = to_ipm(h->opts_ss);
     { Prof p(h, (cudaStream_t)stream, KC_TARGET); k_target<<<nblk(h->B, MPCB_TGT_BLOCK), MPCB_TGT_BLOCK, 0, (cudaStream_t)stream>>>(h->B, par_ss, wss, fss, status, iters, S); }
     CK(cudaGetLastError());
-    CK(cudaStreamSynchronize((cudaStream_t)stream));
-    prof_collect(h);
+    if (h->profile) { CK(cudaStreamSynchronize((cudaStream_t)stream)); prof_collect(h); }
+    h->host_launches += 1; h->last_stream = (cudaStream_t)stream;
     h->last_launches = 1; h->last_ticks = 1;
     return 0;
 #else
@@ -635,12 +805,13 @@ int mpcb_estimate(mpcb_handle_t h, int est_type, const double* y, const double* 
     EstShared E; E.Q = h->Qkf; E.R = h->Rkf; E.K = h->Kest; E.dmin = h->dmin; E.dmax = h->dmax; E.has_dbounds = h->have_dbounds;
     { Prof p(h, (cudaStream_t)stream, KC_ESTIMATE); k_estimate<<<nblk(h->B, 64), 64, 0, (cudaStream_t)stream>>>(h->B, est_type, y, u, t, px, py, xi, P, E); }
     CK(cudaGetLastError());
+    h->host_launches += 1;
     return 0;
 }
 
 int mpcb_model_output(mpcb_handle_t h, const double* x, const double* u, const double* d, const double* t,
                       const double* py, double* y, void* stream) {
-    h->kernel_launches[KC_OTHER] += 1;
+    h->kernel_launches[KC_OTHER] += 1; h->host_launches += 1;
     k_model_output<<<nblk(h->B, 128), 128, 0, (cudaStream_t)stream>>>(h->B, x, u, d, t, py, y);
     CK(cudaGetLastError());
     return 0;
@@ -648,7 +819,7 @@ int mpcb_model_output(mpcb_handle_t h, const double* x, const double* u, const d
 
 int mpcb_model_step(mpcb_handle_t h, const double* x, const double* u, const double* d, const double* t,
                     const double* px, double* xn, void* stream) {
-    h->kernel_launches[KC_OTHER] += 1;
+    h->kernel_launches[KC_OTHER] += 1; h->host_launches += 1;
     k_model_step<<<nblk(h->B, 128), 128, 0, (cudaStream_t)stream>>>(h->B, x, u, d, t, px, xn);
     CK(cudaGetLastError());
     return 0;
@@ -657,7 +828,7 @@ int mpcb_model_step(mpcb_handle_t h, const double* x, const double* u, const dou
 int mpcb_plant_meas(mpcb_handle_t h, const double* x, const double* u, const double* t, const double* pyp,
                     const double* pymp, const double* noise, double* y, void* stream) {
 #if !MPCB_PLANT_NOMINAL
-    h->kernel_launches[KC_OTHER] += 1;
+    h->kernel_launches[KC_OTHER] += 1; h->host_launches += 1;
     k_plant_meas<<<nblk(h->B, 128), 128, 0, (cudaStream_t)stream>>>(h->B, x, u, t, pyp, pymp, noise, y);
     CK(cudaGetLastError());
     return 0;
@@ -669,7 +840,7 @@ int mpcb_plant_meas(mpcb_handle_t h, const double* x, const double* u, const dou
 int mpcb_plant_step(mpcb_handle_t h, double* x, const double* u, const double* t, const double* pxp,
                     const double* pxmp, void* stream) {
 #if !MPCB_PLANT_NOMINAL
-    h->kernel_launches[KC_OTHER] += 1;
+    h->kernel_launches[KC_OTHER] += 1; h->host_launches += 1;
     k_plant_step<<<nblk(h->B, 128), 128, 0, (cudaStream_t)stream>>>(h->B, x, u, t, pxp, pxmp);
     CK(cudaGetLastError());
     return 0;
@@ -685,13 +856,14 @@ int mpcb_set_profiling(mpcb_handle_t h, int on) {
     if (on) while (h->ev_pool.size() < 2 * 1024) { cudaEvent_t e; if (cudaEventCreate(&e) != cudaSuccess) break; h->ev_pool.push_back(e); }
     for (int i = 0; i < MPCB_NKERNELS; ++i) { h->kernel_ms[i] = 0.0; h->kernel_launches[i] = 0; }
     h->eval_instances = h->trial_instances = 0;
-    cudaMemset(h->counters, 0, 2 * sizeof(unsigned long long));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemset(h->counters, 0, 2 * sizeof(unsigned long long)));
     for (StepGroup* g : h->groups) {
         mpcb_ctx* c = g->c;
         c->profile = h->profile;
         for (int i = 0; i < MPCB_NKERNELS; ++i) { c->kernel_ms[i] = 0.0; c->kernel_launches[i] = 0; }
         c->eval_instances = c->trial_instances = 0;
-        cudaMemset(c->counters, 0, 2 * sizeof(unsigned long long));
+        CK(cudaMemset(c->counters, 0, 2 * sizeof(unsigned long long)));
         if (on) while (c->ev_pool.size() < 2 * 1024) { cudaEvent_t e; if (cudaEventCreate(&e) != cudaSuccess) break; c->ev_pool.push_back(e); }
     }
     return 0;
@@ -784,23 +956,20 @@ static int step_impl(mpcb_ctx* h, int est_type, const double* y_meas, const doub
     cudaStream_t s = (cudaStream_t)stream;
     LoopState& L = h->L;
     const int B = h->B, g = nblk(B, 128);
-    int launches = 0;
-    k_step_params<<<g, 128, 0, s>>>(B, px, py, L); launches++;
-    int rc = mpcb_estimate(h, est_type, y_meas, L.u, t, L.px0, L.py0, L.xi, L.P, s); launches++;
+    k_step_params<<<g, 128, 0, s>>>(B, px, py, L);
+    int rc = mpcb_estimate(h, est_type, y_meas, L.u, t, L.px0, L.py0, L.xi, L.P, s);
     if (rc) return rc;
-    k_step_pre<<<g, 128, 0, s>>>(B, t, sp, L, xhat_out, dhat_out); launches++;
-    rc = mpcb_target(h, L.parss, L.wss, L.fss, L.ss_status, L.ss_iters, s); launches++;
+    k_step_pre<<<g, 128, 0, s>>>(B, t, sp, L, xhat_out, dhat_out);
+    rc = mpcb_target(h, L.parss, L.wss, L.fss, L.ss_status, L.ss_iters, s);
     if (rc) return rc;
-    k_step_mid<<<nblk((long)B * 32, 128), 128, 0, s>>>(B, h->loop_first, t, px, py, L, xs_out, us_out); launches++;
+    k_step_mid<<<nblk((long)B * 32, 128), 128, 0, s>>>(B, h->loop_first, t, px, py, L, xs_out, us_out);
     rc = mpcb_ocp(h, L.par, L.w, f_dyn, status_dyn, iters_dyn, s);
     if (rc) return rc;
-    launches += h->last_launches;
-    k_step_post<<<nblk((long)B * 32, 128), 128, 0, s>>>(B, t, status_dyn, L, u_out); launches++;
+    k_step_post<<<nblk((long)B * 32, 128), 128, 0, s>>>(B, t, status_dyn, L, u_out);
     if (status_ss) CK(cudaMemcpyAsync(status_ss, L.ss_status, sizeof(int) * B, cudaMemcpyDeviceToDevice, s));
     CK(cudaGetLastError());
-    h->kernel_launches[KC_OTHER] += 4;
+    h->kernel_launches[KC_OTHER] += 4; h->host_launches += 4;
     h->loop_first = 0;
-    h->last_launches = launches;
     return 0;
 #else
     h->err = "library built without OCP/target"; return -3;
@@ -810,29 +979,14 @@ static int step_impl(mpcb_ctx* h, int est_type, const double* y_meas, const doub
 
 // ---------------------------------------------------------------------------------------------
 // Instance groups.  The solve alternates throughput-bound kernels (stage derivatives) with latency-bound ones (the
-// N-sequential Riccati sweep, the one-thread-per-instance target solve, the tail of ticks in which only a few
-// instances still iterate).  Instances are independent, so the batch can be cut into G contiguous groups, each
-// driven by its own host thread on its own stream: one group's latency-bound phase overlaps another's evaluation.
-// Results are bit-identical to the ungrouped step.  Children alias the parent's buffers at an instance offset.
+// N-sequential Riccati sweep, the target solve, the tail of ticks in which only a few instances still iterate).
+// Instances are independent, so the batch can be cut into G contiguous groups, each queued on its own stream: one group's
+// latency-bound phase overlaps another's evaluation.  Every group's step is a handful of launches plus one CUDA-graph
+// launch, all issued by the calling thread - no worker threads, nobody waits (round 1 needed one polling host thread per
+// group, which made the number of groups a function of the host's core count).  Results are bit-identical to the
+// ungrouped step.  Children alias the parent's buffers at an instance offset.
 // ---------------------------------------------------------------------------------------------
 #if MPCB_HAS_OCP && MPCB_HAS_TARGET
-static void group_worker(StepGroup* g) {
-    cudaSetDevice(g->c->device);
-    std::unique_lock<std::mutex> lk(g->m);
-    while (true) {
-        g->cv.wait(lk, [g] { return g->quit || g->job > g->done; });
-        if (g->quit) return;
-        lk.unlock();
-        const StepArgs& a = g->a;
-        int rc = step_impl(g->c, a.est_type, a.y_meas, a.t, a.sp, a.px, a.py, a.u_out, a.xhat_out, a.dhat_out, a.xs_out,
-                           a.us_out, a.f_dyn, a.status_dyn, a.iters_dyn, a.status_ss, g->s);
-        if (cudaStreamSynchronize(g->s) != cudaSuccess && rc == 0) { g->c->err = "cudaStreamSynchronize failed in a group"; rc = -1; }
-        lk.lock();
-        g->rc = rc; g->done = g->job;
-        g->cv.notify_all();
-    }
-}
-
 static int groups_setup(mpcb_ctx* h) {
     groups_teardown(h);
     const int G = h->ngroups, B = h->B, per = (B + G - 1) / G;
@@ -840,13 +994,24 @@ static int groups_setup(mpcb_ctx* h) {
     for (int b0 = 0; b0 < B; b0 += per) {
         StepGroup* g = new StepGroup();
         g->b0 = b0; g->nb = (b0 + per <= B) ? per : B - b0;
-        mpcb_ctx* c = new mpcb_ctx(*h);                       // constants (bounds, filter matrices) are shared
-        c->groups.clear(); c->ngroups = 1; c->ev_pool.clear(); c->ev_pending.clear(); c->ev_in = nullptr;
+        mpcb_ctx* c = new mpcb_ctx();
+        // constants (bounds, filter matrices) are shared with the parent; everything a solve writes is the group's own
+        c->device = h->device; c->opts_ss = h->opts_ss; c->opts_dyn = h->opts_dyn; c->have_dbounds = h->have_dbounds;
+        c->lbx = h->lbx; c->ubx = h->ubx; c->lbg = h->lbg; c->ubg = h->ubg; c->ss_lbx = h->ss_lbx; c->ss_ubx = h->ss_ubx;
+        c->Qkf = h->Qkf; c->Rkf = h->Rkf; c->Kest = h->Kest; c->dmin = h->dmin; c->dmax = h->dmax;
+        c->loop_mem = h->loop_mem; c->loop_imem = h->loop_imem; c->loop_first = h->loop_first;
+        c->profile = h->profile; c->host_loop = h->host_loop; c->ngroups = 1; c->ev_in = nullptr;
+        c->og_graph = nullptr; c->og_exec = nullptr; c->og_valid = 0; c->host_launches = 0; c->last_stream = nullptr;
+        c->eval_instances = c->trial_instances = 0;
+        for (int i = 0; i < MPCB_NKERNELS; ++i) { c->kernel_ms[i] = 0.0; c->kernel_launches[i] = 0; }
         c->B = g->nb;
         c->ws = h->ws + (size_t)b0 * OcpLayout::total; c->st = h->st + b0;
         if (cudaMalloc(&c->n_active, sizeof(int)) != cudaSuccess || cudaMallocHost(&c->h_active, sizeof(int)) != cudaSuccess ||
-            cudaMalloc(&c->counters, 2 * sizeof(unsigned long long)) != cudaSuccess) { h->err = "group allocation failed"; return -1; }
+            cudaMalloc(&c->counters, 2 * sizeof(unsigned long long)) != cudaSuccess ||
+            cudaMalloc(&c->tick_ctr, 2 * sizeof(unsigned long long)) != cudaSuccess) { h->err = "group allocation failed"; return -1; }
         cudaMemset(c->counters, 0, 2 * sizeof(unsigned long long));
+        cudaMemset(c->tick_ctr, 0, 2 * sizeof(unsigned long long));
+        cudaMemset(c->n_active, 0, sizeof(int));
         const size_t o = (size_t)b0;
         LoopState& L = c->L; const LoopState& P = h->L;
         L.xi = P.xi + o * NXI; L.P = P.P + o * NXI * NXI; L.u = P.u + o * NU; L.us = P.us + o * NU; L.u0 = P.u0 + o * NU;
@@ -855,8 +1020,8 @@ static int groups_setup(mpcb_ctx* h) {
         L.py0 = P.py0 + o * NPY; L.fss = P.fss + o;
         L.dyn_status = P.dyn_status + o; L.ss_status = P.ss_status + o; L.ss_iters = P.ss_iters + o;
         g->c = c;
-        if (cudaStreamCreateWithFlags(&g->s, cudaStreamNonBlocking) != cudaSuccess) { h->err = "group stream creation failed"; return -1; }
-        g->th = std::thread(group_worker, g);
+        if (cudaStreamCreateWithFlags(&g->s, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&g->done, cudaEventDisableTiming) != cudaSuccess) { h->err = "group stream creation failed"; return -1; }
         h->groups.push_back(g);
     }
     return 0;
@@ -866,11 +1031,14 @@ static int groups_setup(mpcb_ctx* h) {
 static void groups_teardown(mpcb_ctx* h) {
 #if MPCB_HAS_OCP && MPCB_HAS_TARGET
     for (StepGroup* g : h->groups) {
-        { std::lock_guard<std::mutex> lk(g->m); g->quit = true; }
-        g->cv.notify_all();
-        if (g->th.joinable()) g->th.join();
-        cudaStreamDestroy(g->s);
-        cudaFree(g->c->n_active); cudaFreeHost(g->c->h_active); cudaFree(g->c->counters);
+        cudaStreamSynchronize(g->s);
+        h->host_launches += g->c->host_launches;              // keep the totals of mpcb_total_launches monotone
+        unsigned long long ctr[2] = {0, 0};
+        cudaMemcpy(ctr, g->c->tick_ctr, sizeof(ctr), cudaMemcpyDeviceToHost);
+        h->host_launches += 4 * (long)ctr[1];
+        cudaStreamDestroy(g->s); cudaEventDestroy(g->done);
+        ocp_graph_drop(g->c);
+        cudaFree(g->c->n_active); cudaFreeHost(g->c->h_active); cudaFree(g->c->counters); cudaFree(g->c->tick_ctr);
         for (auto e : g->c->ev_pool) cudaEventDestroy(e);
         delete g->c; delete g;
     }
@@ -884,47 +1052,75 @@ int mpcb_set_groups(mpcb_handle_t h, int n) {
     return 0;
 }
 
+// Asynchronous: every launch of the step is queued behind the caller's work on `stream`, and `stream` is made to wait for
+// the step's completion; the call returns without waiting.  Read the outputs in stream order (or after synchronising).
 int mpcb_step(mpcb_handle_t h, int est_type, const double* y_meas, const double* t, const double* sp, const double* px,
               const double* py, double* u_out, double* xhat_out, double* dhat_out, double* xs_out, double* us_out,
               double* f_dyn, int* status_dyn, int* iters_dyn, int* status_ss, void* stream) {
 #if MPCB_HAS_OCP && MPCB_HAS_TARGET
+    h->last_stream = (cudaStream_t)stream;
     if (h->ngroups <= 1)
         return step_impl(h, est_type, y_meas, t, sp, px, py, u_out, xhat_out, dhat_out, xs_out, us_out, f_dyn, status_dyn,
                          iters_dyn, status_ss, stream);
     if (!h->loop_mem) { h->err = "mpcb_loop_reset has not been called"; return -2; }
     if (h->groups.empty()) { int rc = groups_setup(h); if (rc) return rc; }
     CK(cudaEventRecord(h->ev_in, (cudaStream_t)stream));      // the groups start after the caller's work on `stream`
+    int rc = 0;
     for (StepGroup* g : h->groups) {
         const size_t o = (size_t)g->b0;
         mpcb_ctx* c = g->c;
         c->opts_ss = h->opts_ss; c->opts_dyn = h->opts_dyn; c->have_dbounds = h->have_dbounds; c->loop_first = h->loop_first;
         c->profile = h->profile;
         CK(cudaStreamWaitEvent(g->s, h->ev_in, 0));
-        StepArgs a;
-        a.est_type = est_type; a.y_meas = y_meas + o * NY; a.t = t + o; a.sp = sp + o * (NU + NY + NX);
-        a.px = px ? px + o * NPX * NH : nullptr; a.py = py ? py + o * NPY * NH : nullptr;
-        a.u_out = u_out + o * NU; a.xhat_out = xhat_out + o * NX; a.dhat_out = dhat_out + o * ND; a.xs_out = xs_out + o * NX;
-        a.us_out = us_out + o * NU; a.f_dyn = f_dyn + o; a.status_dyn = status_dyn + o; a.iters_dyn = iters_dyn + o;
-        a.status_ss = status_ss ? status_ss + o : nullptr;
-        { std::lock_guard<std::mutex> lk(g->m); g->a = a; g->job += 1; }
-        g->cv.notify_all();
+        const int r = step_impl(c, est_type, y_meas + o * NY, t + o, sp + o * (NU + NY + NX), px ? px + o * NPX * NH : nullptr,
+                                py ? py + o * NPY * NH : nullptr, u_out + o * NU, xhat_out + o * NX, dhat_out + o * ND,
+                                xs_out + o * NX, us_out + o * NU, f_dyn + o, status_dyn + o, iters_dyn + o,
+                                status_ss ? status_ss + o : nullptr, g->s);
+        if (r && !rc) { rc = r; h->err = c->err; }
+        CK(cudaEventRecord(g->done, g->s));
+        CK(cudaStreamWaitEvent((cudaStream_t)stream, g->done, 0));
     }
-    int rc = 0, launches = 0, ticks = 0;
-    for (StepGroup* g : h->groups) {
-        std::unique_lock<std::mutex> lk(g->m);
-        g->cv.wait(lk, [g] { return g->done == g->job; });
-        if (g->rc && !rc) { rc = g->rc; h->err = g->c->err; }
-        launches += g->c->last_launches; ticks = ticks > g->c->last_ticks ? ticks : g->c->last_ticks;
-    }
-    // the groups have synchronised their streams: every output is complete when this returns
-    h->loop_first = 0; h->last_launches = launches; h->last_ticks = ticks;
+    h->loop_first = 0;
     return rc;
 #else
     h->err = "library built without OCP/target"; return -3;
 #endif
 }
 
+// Counters.  The device-driven solve counts its ticks on the device, so these wait for the handle's last stream first.
+static void read_ticks(mpcb_ctx* h, unsigned long long* last, unsigned long long* total) {
+    unsigned long long ctr[2] = {0, 0};
+    cudaStreamSynchronize(h->last_stream);
+    cudaMemcpy(ctr, h->tick_ctr, sizeof(ctr), cudaMemcpyDeviceToHost);
+    *last = ctr[0]; *total = ctr[1];
+}
+
+int mpcb_last_ticks(mpcb_handle_t h) {
+    if (h->last_ticks >= 0 && h->groups.empty()) return h->last_ticks;       // host-polled solve: counted on the host
+    unsigned long long last = 0, total = 0, worst = 0;
+    if (h->groups.empty()) { read_ticks(h, &last, &total); return (int)last; }
+    for (StepGroup* g : h->groups) {
+        cudaStreamSynchronize(g->s);
+        if (g->c->last_ticks >= 0) { worst = worst > (unsigned long long)g->c->last_ticks ? worst : (unsigned long long)g->c->last_ticks; continue; }
+        read_ticks(g->c, &last, &total);
+        worst = worst > last ? worst : last;
+    }
+    return (int)worst;
+}
+
+// kernel launches made through this handle since its creation (host launches + 5 per device-driven tick)
+long mpcb_total_launches(mpcb_handle_t h) {
+    unsigned long long last = 0, total = 0;
+    read_ticks(h, &last, &total);
+    long n = h->host_launches + 4 * (long)total;
+    for (StepGroup* g : h->groups) {
+        cudaStreamSynchronize(g->s);
+        read_ticks(g->c, &last, &total);
+        n += g->c->host_launches + 4 * (long)total;
+    }
+    return n;
+}
+
 int mpcb_last_launches(mpcb_handle_t h) { return h->last_launches; }
-int mpcb_last_ticks(mpcb_handle_t h) { return h->last_ticks; }
 
 }  // extern "C"

@@ -34,7 +34,7 @@ class MpcbOpts(ctypes.Structure):
 C_SYMBOLS = ("mpcb_abi_version", "mpcb_default_opts", "mpcb_get_dims", "mpcb_model_flops", "mpcb_create",
              "mpcb_destroy", "mpcb_last_error", "mpcb_set_const", "mpcb_estimate", "mpcb_target", "mpcb_ocp",
              "mpcb_plant_meas", "mpcb_plant_step", "mpcb_model_output", "mpcb_model_step", "mpcb_stage_derivs",
-             "mpcb_last_launches", "mpcb_last_ticks", "mpcb_set_groups", "mpcb_set_profiling", "mpcb_get_profile", "mpcb_dfma_peak",
+             "mpcb_last_launches", "mpcb_last_ticks", "mpcb_total_launches", "mpcb_set_groups", "mpcb_set_profiling", "mpcb_get_profile", "mpcb_dfma_peak",
              "mpcb_loop_reset", "mpcb_step", "mpcb_loop_get")
 
 
@@ -65,6 +65,7 @@ class MpcbLibrary:
         L.mpcb_model_step.argtypes = [vp] * 8
         L.mpcb_stage_derivs.argtypes = [vp] * 9
         L.mpcb_last_launches.argtypes = [vp]; L.mpcb_last_ticks.argtypes = [vp]
+        L.mpcb_total_launches.argtypes = [vp]; L.mpcb_total_launches.restype = ctypes.c_long
         L.mpcb_set_groups.argtypes = [vp, ctypes.c_int]
         L.mpcb_set_profiling.argtypes = [vp, ci]
         L.mpcb_get_profile.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_long),
@@ -111,7 +112,6 @@ class MpcbHandle:
         with torch.cuda.device(self.device):
             rc = self.L.mpcb_create(self.batch, ctypes.byref(oss), ctypes.byref(ody), ctypes.byref(self._h))
         self._check(rc)
-        self.launches = 0
 
     def _check(self, rc):
         if rc != 0:
@@ -162,7 +162,6 @@ class MpcbHandle:
         par = self.tensor(par, d.npar); w = self.tensor(w, d.nw).clone()
         f = self.empty(self.batch); st = self.empty(self.batch, dtype=torch.int32); it = self.empty(self.batch, dtype=torch.int32)
         self._check(self.L.mpcb_ocp(self._h, par.data_ptr(), w.data_ptr(), f.data_ptr(), st.data_ptr(), it.data_ptr(), self._stream()))
-        self.launches += self.L.mpcb_last_launches(self._h)
         return w, f, st, it
 
     def target(self, par_ss, wss):
@@ -171,7 +170,6 @@ class MpcbHandle:
         par_ss = self.tensor(par_ss, d.nparss); wss = self.tensor(wss, d.nwss).clone()
         f = self.empty(self.batch); st = self.empty(self.batch, dtype=torch.int32); it = self.empty(self.batch, dtype=torch.int32)
         self._check(self.L.mpcb_target(self._h, par_ss.data_ptr(), wss.data_ptr(), f.data_ptr(), st.data_ptr(), it.data_ptr(), self._stream()))
-        self.launches += 1
         return wss, f, st, it
 
     def estimate(self, est_type, y, u_prev, t, px, py, xi, P):
@@ -181,7 +179,6 @@ class MpcbHandle:
         xi = self.tensor(xi, d.nxi).clone(); P = self.tensor(P, d.nxi * d.nxi).clone()
         self._check(self.L.mpcb_estimate(self._h, int(est_type), y.data_ptr(), u_prev.data_ptr(), t.data_ptr(), px.data_ptr(),
                                          py.data_ptr(), xi.data_ptr(), P.data_ptr(), self._stream()))
-        self.launches += 1
         return xi, P
 
     def model_output(self, x, u, dd, t, py):
@@ -190,7 +187,6 @@ class MpcbHandle:
         t = self.tensor(t, 1); py = self.tensor(py, d.npy)
         y = self.empty(self.batch, d.ny)
         self._check(self.L.mpcb_model_output(self._h, x.data_ptr(), u.data_ptr(), dd.data_ptr(), t.data_ptr(), py.data_ptr(), y.data_ptr(), self._stream()))
-        self.launches += 1
         return y
 
     def model_step(self, x, u, dd, t, px):
@@ -199,7 +195,6 @@ class MpcbHandle:
         t = self.tensor(t, 1); px = self.tensor(px, d.npx)
         xn = self.empty(self.batch, d.nx)
         self._check(self.L.mpcb_model_step(self._h, x.data_ptr(), u.data_ptr(), dd.data_ptr(), t.data_ptr(), px.data_ptr(), xn.data_ptr(), self._stream()))
-        self.launches += 1
         return xn
 
     def plant_meas(self, x, u, t, pyp, pymp, noise=None):
@@ -210,7 +205,6 @@ class MpcbHandle:
         y = self.empty(self.batch, d.ny)
         self._check(self.L.mpcb_plant_meas(self._h, x.data_ptr(), u.data_ptr(), t.data_ptr(), pyp.data_ptr(), pymp.data_ptr(),
                                            nz.data_ptr() if nz is not None else None, y.data_ptr(), self._stream()))
-        self.launches += 1
         return y
 
     def plant_step(self, x, u, t, pxp, pxmp):
@@ -218,7 +212,6 @@ class MpcbHandle:
         x = self.tensor(x, d.nxp).clone(); u = self.tensor(u, d.nu); t = self.tensor(t, 1)
         pxp = self.tensor(pxp, d.npxp); pxmp = self.tensor(pxmp, d.npxp)
         self._check(self.L.mpcb_plant_step(self._h, x.data_ptr(), u.data_ptr(), t.data_ptr(), pxp.data_ptr(), pxmp.data_ptr(), self._stream()))
-        self.launches += 1
         return x
 
     def stage_derivs(self, par, w, lam):
@@ -229,7 +222,6 @@ class MpcbHandle:
         c = self.empty(self.batch, d.N, d.nx); H = self.empty(self.batch, d.N, nz * (nz + 1) // 2)
         self._check(self.L.mpcb_stage_derivs(self._h, par.data_ptr(), w.data_ptr(), lam.data_ptr(), A.data_ptr(), Bm.data_ptr(),
                                              c.data_ptr(), H.data_ptr(), self._stream()))
-        self.launches += 1
         return A, Bm, c, H
 
     # -- fused closed-loop step ---------------------------------------------------
@@ -260,7 +252,6 @@ class MpcbHandle:
                                      o["u"].data_ptr(), o["xhat"].data_ptr(), o["dhat"].data_ptr(), o["xs"].data_ptr(),
                                      o["us"].data_ptr(), o["f"].data_ptr(), o["status"].data_ptr(), o["iters"].data_ptr(),
                                      o["status_ss"].data_ptr(), self._stream()))
-        self.launches += self.L.mpcb_last_launches(self._h)
         return o
 
     def set_groups(self, n: int):
@@ -276,7 +267,13 @@ class MpcbHandle:
 
     @property
     def last_ticks(self):
+        """Solver ticks of the last OCP solve (waits for it: the count lives on the device)."""
         return self.L.mpcb_last_ticks(self._h)
+
+    @property
+    def launches(self):
+        """Kernel launches made through this handle so far, the device-driven solver ticks included (synchronises)."""
+        return int(self.L.mpcb_total_launches(self._h))
 
     KERNEL_CLASSES = ("ocp_init", "ocp_eval", "ocp_kkt", "ocp_trial", "ocp_accept", "target", "estimate", "other")
 

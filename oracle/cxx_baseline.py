@@ -30,6 +30,7 @@ def build(name, prob, ss, ocp):
             hsh.update(fh.read())
     with open(os.path.join(HERE, "cxx_loop.cpp"), "rb") as fh:
         hsh.update(fh.read())
+    hsh.update(_cpu_flags().encode())        # -march=native: a library built on another host CPU must not be reused
     digest = hsh.hexdigest()[:16]
     work = os.path.join(BUILD, "cxx_%s_%s" % (name, digest))
     so = os.path.join(BUILD, "cxx_%s_%s.so" % (name, digest))
@@ -45,6 +46,17 @@ def build(name, prob, ss, ocp):
                         "-I", work, "-I", CSRC, "-o", tmp, os.path.join(HERE, "cxx_loop.cpp")], check=True)
         os.replace(tmp, so)
     return so
+
+
+def _cpu_flags() -> str:
+    try:
+        with open("/proc/cpuinfo") as fh:
+            for line in fh:
+                if line.startswith("flags"):
+                    return line
+    except OSError:
+        pass
+    return ""
 
 
 class CxxLoop:
