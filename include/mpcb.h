@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define MPCB_ABI_VERSION 1
+#define MPCB_ABI_VERSION 2
 
 typedef struct mpcb_ctx* mpcb_handle_t;
 
@@ -141,6 +141,12 @@ int  mpcb_loop_get(mpcb_handle_t h, double* xi, double* P, double* u, void* stre
  * another.  Results do not change (instances are independent - the reference solves them one after another,
  * MPC_code.py:485).  The caller's stream is made to wait for all groups.  Default 1. */
 int  mpcb_set_groups(mpcb_handle_t h, int n);
+
+/* Policy of the fused step for FAILED solves (status < 0: Maximum_Iterations_Exceeded, Restoration_Failed,
+ * Error_In_Step_Computation).  0 (default) = the reference's behaviour: only Infeasible_Problem_Detected is rejected, any
+ * other iterate is applied to the plant (MPC_code.py:786).  1 = hold: treat them like an infeasible solve (previous input
+ * kept, estimate propagated with the model, warm start kept; MPC_code.py:804-805). */
+int  mpcb_set_policy(mpcb_handle_t h, int hold_failed);
 
 /* Profiling.  With profiling on, every kernel launch is bracketed by CUDA events on its stream and the
  * time is accumulated per kernel class: 0 ocp_init, 1 ocp_eval (stage derivatives), 2 ocp_kkt (Riccati

@@ -332,12 +332,16 @@ __global__ void k_step_mid(int B, int first, const double* t, const double* px, 
 }
 
 // after the OCP: status gate, u_k and x(k+1|k) extraction or model fallback (:786-805); one warp per instance
-__global__ void k_step_post(int B, const double* t, const int* status, LoopState L, double* u_out) {
+// hold_failed: treat every failed solve (status < 0: iteration limit, restoration failed, step computation) like an
+// infeasible one - keep the previous input and propagate the estimate with the model.  The reference applies such
+// iterates to the plant (only 'Infeasible_Problem_Detected' is rejected, MPC_code.py:786); that stays the default.
+__global__ void k_step_post(int B, const double* t, const int* status, LoopState L, double* u_out, int hold_failed) {
     const int inst = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (inst >= B) return;
     double* xi = L.xi + (size_t)inst * NXI; double* u = L.u + (size_t)inst * NU;
     const double* w = L.w + (size_t)inst * NW;
-    const int st = status[inst];
+    int st = status[inst];
+    if (hold_failed && st < 0 && st != -13) st = 2;
     if (lane == 0) L.dyn_status[inst] = st;
     if (st == -13) {                                      // diverged instance (NaN state): frozen, u keeps its value
         for (int i = lane; i < NU; i += 32) u_out[(size_t)inst * NU + i] = u[i];
@@ -376,6 +380,7 @@ struct mpcb_ctx {
     double* stage_mem; int* stage_imem;      // staging copies of par | w | f and status | iters for callers whose buffers move
     unsigned long long* tick_ctr;            // device: {ticks of the last solve, ticks since creation}
     long host_launches; int host_loop; cudaStream_t last_stream;
+    int hold_failed;                         // mpcb_set_policy
     // loop state of the fused step (mpcb_loop_reset / mpcb_step)
     double* loop_mem; int* loop_imem; int loop_first;
 #if MPCB_HAS_OCP && MPCB_HAS_TARGET
@@ -477,7 +482,7 @@ int mpcb_create(int batch, const mpcb_opts_t* oss, const mpcb_opts_t* odyn, mpcb
     mpcb_ctx* h = new mpcb_ctx();
     h->B = batch; h->have_dbounds = 0; h->last_launches = 0; h->last_ticks = 0;
     h->og_graph = nullptr; h->og_exec = nullptr; h->og_valid = 0; h->tick_ctr = nullptr; h->host_launches = 0; h->last_stream = nullptr;
-    h->stage_mem = nullptr; h->stage_imem = nullptr;
+    h->stage_mem = nullptr; h->stage_imem = nullptr; h->hold_failed = 0;
     { const char* e = getenv("MPCB_HOST_LOOP"); h->host_loop = (e && e[0] == '1') ? 1 : 0; }
     mpcb_default_opts(&h->opts_ss); mpcb_default_opts(&h->opts_dyn);
     if (oss) h->opts_ss = *oss;
@@ -965,7 +970,7 @@ static int step_impl(mpcb_ctx* h, int est_type, const double* y_meas, const doub
     k_step_mid<<<nblk((long)B * 32, 128), 128, 0, s>>>(B, h->loop_first, t, px, py, L, xs_out, us_out);
     rc = mpcb_ocp(h, L.par, L.w, f_dyn, status_dyn, iters_dyn, s);
     if (rc) return rc;
-    k_step_post<<<nblk((long)B * 32, 128), 128, 0, s>>>(B, t, status_dyn, L, u_out);
+    k_step_post<<<nblk((long)B * 32, 128), 128, 0, s>>>(B, t, status_dyn, L, u_out, h->hold_failed);
     if (status_ss) CK(cudaMemcpyAsync(status_ss, L.ss_status, sizeof(int) * B, cudaMemcpyDeviceToDevice, s));
     CK(cudaGetLastError());
     h->kernel_launches[KC_OTHER] += 4; h->host_launches += 4;
@@ -1000,7 +1005,7 @@ static int groups_setup(mpcb_ctx* h) {
         c->lbx = h->lbx; c->ubx = h->ubx; c->lbg = h->lbg; c->ubg = h->ubg; c->ss_lbx = h->ss_lbx; c->ss_ubx = h->ss_ubx;
         c->Qkf = h->Qkf; c->Rkf = h->Rkf; c->Kest = h->Kest; c->dmin = h->dmin; c->dmax = h->dmax;
         c->loop_mem = h->loop_mem; c->loop_imem = h->loop_imem; c->loop_first = h->loop_first;
-        c->profile = h->profile; c->host_loop = h->host_loop; c->ngroups = 1; c->ev_in = nullptr;
+        c->profile = h->profile; c->host_loop = h->host_loop; c->ngroups = 1; c->ev_in = nullptr; c->hold_failed = h->hold_failed;
         c->og_graph = nullptr; c->og_exec = nullptr; c->og_valid = 0; c->host_launches = 0; c->last_stream = nullptr;
         c->eval_instances = c->trial_instances = 0;
         for (int i = 0; i < MPCB_NKERNELS; ++i) { c->kernel_ms[i] = 0.0; c->kernel_launches[i] = 0; }
@@ -1046,6 +1051,8 @@ static void groups_teardown(mpcb_ctx* h) {
     h->groups.clear();
 }
 
+int mpcb_set_policy(mpcb_handle_t h, int hold_failed) { h->hold_failed = hold_failed ? 1 : 0; return 0; }
+
 int mpcb_set_groups(mpcb_handle_t h, int n) {
     if (n < 1 || n > h->B) { h->err = "mpcb_set_groups: need 1 <= n <= batch"; return -2; }
     if (n != h->ngroups) { groups_teardown(h); h->ngroups = n; }
@@ -1070,7 +1077,7 @@ int mpcb_step(mpcb_handle_t h, int est_type, const double* y_meas, const double*
         const size_t o = (size_t)g->b0;
         mpcb_ctx* c = g->c;
         c->opts_ss = h->opts_ss; c->opts_dyn = h->opts_dyn; c->have_dbounds = h->have_dbounds; c->loop_first = h->loop_first;
-        c->profile = h->profile;
+        c->profile = h->profile; c->hold_failed = h->hold_failed;
         CK(cudaStreamWaitEvent(g->s, h->ev_in, 0));
         const int r = step_impl(c, est_type, y_meas + o * NY, t + o, sp + o * (NU + NY + NX), px ? px + o * NPX * NH : nullptr,
                                 py ? py + o * NPY * NH : nullptr, u_out + o * NU, xhat_out + o * NX, dhat_out + o * ND,

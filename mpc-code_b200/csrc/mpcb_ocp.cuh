@@ -40,7 +40,9 @@ struct IpmOpts {       // IPOPT option names; values set from mpcb_opts_t, the r
 
 struct InstState {
     double mu, tau, alpha, alpha_z, theta, phi, gphid, amin, theta0, dw_last, fval, E0;
+    double theta_entry;                   // violation at which the feasibility restoration was entered
     int    state, iter, status, nfilt, acc_cnt, ls_iter;
+    int    resto, resto_calls;            // in restoration / number of times it was entered in this solve
     double filt[2 * MPCB_MAXFILT];
 };
 
@@ -223,6 +225,7 @@ MPCB_HD void ocp_init_stage(OcpInst& I, const OcpShared& S, int k) {
         st.mu = S.o.mu_init; st.tau = fmax(0.99, 1.0 - S.o.mu_init);
         st.alpha = st.alpha_z = 0.0; st.theta0 = -1.0; st.dw_last = 0.0; st.fval = 0.0; st.E0 = 0.0;
         st.state = ST_EVAL; st.iter = 0; st.status = -1; st.nfilt = 0; st.acc_cnt = 0; st.ls_iter = 0;
+        st.resto = 0; st.resto_calls = 0; st.theta_entry = 0.0;
         // a non-finite estimate / target / disturbance (diverged instance) cannot be evaluated: IPOPT's
         // Invalid_Number_Detected (-13), decided here so that the instance does not burn line-search ticks
         double chk = 0.0;
@@ -277,14 +280,17 @@ MPCB_HD void ocp_export_stage(OcpInst& I, int k) {
 // eval: derivatives of stage k at the current iterate, condensed into the stage record
 // (k = 0..NH-1; k = NH-1 also writes the terminal record)
 // =============================================================================================
-MPCB_HD void bound_terms(double v, double lo, double hi, double zl, double zu, double rf, bool active,
+// rmu > 0: restoration mode - the multipliers are not iterated, the primal barrier Hessian mu / d^2 is used (z = mu / d)
+MPCB_HD void bound_terms(double v, double lo, double hi, double zl, double zu, double rf, bool active, double rmu,
                          double* iL, double* iU, double* zL, double* zU, double* qL, double* qU, double* sig,
                          double* zsum, double* nb, double* pmin, double* pmax, double* prod) {
     *iL = *iU = *zL = *zU = *qL = *qU = 0.0;
     if (!active) return;
-    if (fin(lo)) { const double d = v - rlo(lo, rf); const double id = MPCB_RCP(d); *iL = id; *zL = zl; *qL = id * MPCB_RCP(zl); *sig += zl * id;
+    if (fin(lo)) { const double d = v - rlo(lo, rf); const double id = MPCB_RCP(d); if (rmu > 0.0) zl = rmu * id;
+                   *iL = id; *zL = zl; *qL = id * MPCB_RCP(zl); *sig += zl * id;
                    *zsum += zl; *nb += 1.0; *pmin = fmin(*pmin, d * zl); *pmax = fmax(*pmax, d * zl); *prod *= d; }
-    if (fin(hi)) { const double d = rhi(hi, rf) - v; const double id = MPCB_RCP(d); *iU = id; *zU = zu; *qU = id * MPCB_RCP(zu); *sig += zu * id;
+    if (fin(hi)) { const double d = rhi(hi, rf) - v; const double id = MPCB_RCP(d); if (rmu > 0.0) zu = rmu * id;
+                   *iU = id; *zU = zu; *qU = id * MPCB_RCP(zu); *sig += zu * id;
                    *zsum += zu; *nb += 1.0; *pmin = fmin(*pmin, d * zu); *pmax = fmax(*pmax, d * zu); *prod *= d; }
 }
 
@@ -382,6 +388,21 @@ MPCB_HD void ocp_eval_stage(OcpInst& I, const OcpShared& S, int k, RkBuf rb = Rk
 #else
     double* r = I.rec + k * REC_SZ;
 #endif
+    // Feasibility restoration (entered by ocp_accept when the line search fails): the step minimises
+    //   zeta/2 |D_R dv|^2 - mu sum log(slacks to the bounds)   subject to the linearised constraints,
+    // zeta = sqrt(mu), D_R = diag(1 / max(1, |v|)): no cost gradient, Hessian zeta D_R^2, primal barrier terms.
+    const bool resto = I.st->resto != 0;
+    const double rmu = resto ? I.st->mu : 0.0, zeta = resto ? sqrt(I.st->mu) : 0.0;
+    if (resto) {
+#pragma unroll
+        for (int i = 0; i < NZAP; ++i) Hp[i] = 0.0;
+#pragma unroll
+        for (int j = 0; j < NZA; ++j) {
+            const double vj = w[k * NZA + j], sc = fmax(1.0, fabs(vj));
+            Hp[tri(j, j)] = zeta / (sc * sc);
+            g[j] = 0.0;
+        }
+    }
     double th = 0.0, prim = 0.0, ysum = 0.0, zsum = 0.0, nb = 0.0, pmin = 1e300, pmax = -1e300;
     double prod = 1.0;     // product of all slacks-to-bounds of the stage: one log instead of one per bound
 #pragma unroll
@@ -405,7 +426,7 @@ MPCB_HD void ocp_eval_stage(OcpInst& I, const OcpShared& S, int k, RkBuf rb = Rk
         const int wi = k * NZA + j;
         const bool active = !(k == 0 && j < NXA);          // x_0 is fixed
         double iL, iU, zL, zU, qL, qU;
-        bound_terms(w[wi], S.lbx[wi], S.ubx[wi], I.zL[wi], I.zU[wi], rf, active, &iL, &iU, &zL, &zU, &qL, &qU, &dg[j], &zsum, &nb, &pmin, &pmax, &prod);
+        bound_terms(w[wi], S.lbx[wi], S.ubx[wi], I.zL[wi], I.zU[wi], rf, active, rmu, &iL, &iU, &zL, &zU, &qL, &qU, &dg[j], &zsum, &nb, &pmin, &pmax, &prod);
         r[R_IL + j] = iL; r[R_IU + j] = iU; r[R_QL + j] = qL; r[R_QU + j] = qU; r[R_GL + j] = g[j];
         res[j] += zU - zL;
     }
@@ -421,17 +442,20 @@ MPCB_HD void ocp_eval_stage(OcpInst& I, const OcpShared& S, int k, RkBuf rb = Rk
         for (int i = 0; i < NG; ++i) mult[i] = I.ym[k * NG + i];
         ocp_out_d(z, u, I.par, px, py, mult, Y, JY, HY);
 #if !MPCB_OUT_LINEAR
+        if (!resto) {
 #pragma unroll
-        for (int j = 0; j < NZA; ++j)
+            for (int j = 0; j < NZA; ++j)
 #pragma unroll
-            for (int i = 0; i < NZA; ++i) M[i + NZA * j] += HY[tri(i, j)];
+                for (int i = 0; i < NZA; ++i) M[i + NZA * j] += HY[tri(i, j)];
+        }
 #endif
 #pragma unroll
         for (int q = 0; q < NG; ++q) {
             const int gi = k * NG + q;
             const double sv = I.s[gi], lo = S.lbg[gi], hi = S.ubg[gi];
             double isl, isu, vl, vu, qsl, qsu, sig = 0.0;
-            bound_terms(sv, lo, hi, I.vL[gi], I.vU[gi], rf, true, &isl, &isu, &vl, &vu, &qsl, &qsu, &sig, &zsum, &nb, &pmin, &pmax, &prod);
+            bound_terms(sv, lo, hi, I.vL[gi], I.vU[gi], rf, true, rmu, &isl, &isu, &vl, &vu, &qsl, &qsu, &sig, &zsum, &nb, &pmin, &pmax, &prod);
+            if (resto) { const double sc = fmax(1.0, fabs(sv)); sig += zeta / (sc * sc); }
             const double rg = Y[q] - sv;
             r[R_SG + q] = sig; r[R_ISL + q] = isl; r[R_ISU + q] = isu;
             r[R_QSL + q] = qsl; r[R_QSU + q] = qsu;
@@ -480,8 +504,8 @@ MPCB_HD void ocp_eval_stage(OcpInst& I, const OcpShared& S, int k, RkBuf rb = Rk
         for (int j = 0; j < NXA; ++j) {
             const int wi = NH * NZA + j;
             double iL, iU, zL, zU, qL, qU, sig = 0.0;
-            bound_terms(w[wi], S.lbx[wi], S.ubx[wi], I.zL[wi], I.zU[wi], rf, true, &iL, &iU, &zL, &zU, &qL, &qU, &sig, &zs, &nbn, &pmn, &pmx, &prodN);
-            const double gj = (j < NX) ? gN[j] : 0.0;
+            bound_terms(w[wi], S.lbx[wi], S.ubx[wi], I.zL[wi], I.zU[wi], rf, true, rmu, &iL, &iU, &zL, &zU, &qL, &qU, &sig, &zs, &nbn, &pmn, &pmx, &prodN);
+            const double gj = (resto || j >= NX) ? 0.0 : gN[j];
             t[T_IL + j] = iL; t[T_IU + j] = iU; t[T_ZL + j] = zL; t[T_ZU + j] = zU; t[T_QL + j] = qL; t[T_QU + j] = qU; t[T_GN + j] = gj;
             double dr = gj - lam[j] + zU - zL;                           // lam = lam_N for k = NH-1
 #if MPCB_TERMCONS
@@ -489,7 +513,11 @@ MPCB_HD void ocp_eval_stage(OcpInst& I, const OcpShared& S, int k, RkBuf rb = Rk
 #endif
             dualN = fmax(dualN, fabs(dr));
 #pragma unroll
-            for (int i = 0; i < NXA; ++i) t[T_H + i + NXA * j] = (i < NX && j < NX) ? HN[tri(i, j)] : 0.0;
+            for (int i = 0; i < NXA; ++i) {
+                double hij = (i < NX && j < NX) ? HN[tri(i, j)] : 0.0;
+                if (resto) { const double sc = fmax(1.0, fabs(w[wi])); hij = (i == j) ? zeta / (sc * sc) : 0.0; }
+                t[T_H + i + NXA * j] = hij;
+            }
         }
         double thT = 0.0, primT = 0.0, ysT = 0.0;
 #if MPCB_TERMCONS
@@ -835,22 +863,25 @@ MPCB_HD void ocp_kkt(OcpInst& I, const OcpShared& S, double* sm) {
     const double c0 = bounded ? fmax(fabs(pmax), fabs(pmin)) : 0.0;
     const double E0 = fmax(fmax(dual / sd, prim), c0 / sc);
     int acc_cnt = st.acc_cnt;
+    const bool resto = st.resto != 0;     // restoration iteration: no termination test, no barrier update (see ocp_accept)
     W_SYNC();
     if (lane == 0) st.E0 = E0;
     if (!(E0 == E0) || !fin(E0)) { ocp_finish(I, S, -13, fobj); return; }
-    if (E0 <= S.o.tol && dual <= 1.0 && prim <= 1e-4 && c0 <= 1e-4) { ocp_finish(I, S, 0, fobj); return; }
-    if (E0 <= S.o.acceptable_tol && dual <= 1e10 && prim <= 1e-2 && c0 <= 1e-2) {
-        acc_cnt += 1;
-        if (acc_cnt >= S.o.acceptable_iter) { ocp_finish(I, S, 1, fobj); return; }
-    } else {
-        acc_cnt = 0;
+    if (!resto) {
+        if (E0 <= S.o.tol && dual <= 1.0 && prim <= 1e-4 && c0 <= 1e-4) { ocp_finish(I, S, 0, fobj); return; }
+        if (E0 <= S.o.acceptable_tol && dual <= 1e10 && prim <= 1e-2 && c0 <= 1e-2) {
+            acc_cnt += 1;
+            if (acc_cnt >= S.o.acceptable_iter) { ocp_finish(I, S, 1, fobj); return; }
+        } else {
+            acc_cnt = 0;
+        }
     }
     if (iter >= S.o.max_iter) { ocp_finish(I, S, -1, fobj); return; }
     // ---- monotone barrier update (kappa_eps=10, kappa_mu=0.2, theta_mu=1.5)
     double mu = st.mu;
     const double mu_min = S.o.tol / 10.0;
     bool changed = false;
-    while (mu > mu_min) {
+    while (!resto && mu > mu_min) {
         const double cm = bounded ? fmax(fabs(pmax - mu), fabs(pmin - mu)) : 0.0;
         const double Emu = fmax(fmax(dual / sd, prim), cm / sc);
         if (Emu > 10.0 * mu) break;
@@ -1168,16 +1199,70 @@ MPCB_HD void ocp_accept(OcpInst& I, const OcpShared& S) {
         }
     }
     const double amin = st.amin;
+    const int resto = st.resto, resto_calls = st.resto_calls;
+    const double theta_entry = st.theta_entry;
     W_SYNC();
+    if (resto) {
+        // ---- restoration iteration (proximal Gauss-Newton step on the constraint violation, see ocp_eval_stage):
+        //      Armijo backtracking on the violation alone; multipliers restart from zero / mu over the slack; back to
+        //      the regular iterations once the violation is kappa_resto = 0.9 of its value at entry and the filter
+        //      (which holds the entry point) accepts the new point
+        // a step shorter than 1e-5 of the Gauss-Newton step (jammed against the bounds, or no descent): the violation
+        // cannot be reduced - a stationary point of the infeasibility (IPOPT: Infeasible_Problem_Detected)
+        if (!(alpha > 1e-5)) { ocp_finish_w(I, S, theta > 1e-4 ? 2 : -2, st.fval); return; }
+        const bool fine = (th_t == th_t) && fin(th_t) && th_t <= (1.0 - 1e-4 * alpha) * theta;
+        if (!fine) {
+            if (lane == 0) { st.alpha = 0.5 * alpha; st.ls_iter += 1; }
+            W_SYNC();
+            return;
+        }
+        for (int i = NXA + lane; i < NWI; i += N_LANES) {
+            const double lo = S.lbx[i], hi = S.ubx[i];
+            const double wn = I.w[i] + alpha * I.dw[i];
+            if (fin(lo)) I.zL[i] = mu / (wn - rlo(lo, rf));
+            if (fin(hi)) I.zU[i] = mu / (rhi(hi, rf) - wn);
+            I.w[i] = wn;
+        }
+        for (int i = lane; i < NH * NXA; i += N_LANES) I.lam[i] = 0.0;
+        for (int i = lane; i < NXT; i += N_LANES) I.nuT[i] = 0.0;
+#if NG > 0
+        for (int i = lane; i < NH * NG; i += N_LANES) {
+            const double lo = S.lbg[i], hi = S.ubg[i];
+            const double sn = I.s[i] + alpha * I.ds[i];
+            if (fin(lo)) I.vL[i] = mu / (sn - rlo(lo, rf));
+            if (fin(hi)) I.vU[i] = mu / (rhi(hi, rf) - sn);
+            I.s[i] = sn;
+            I.ym[i] = 0.0;
+        }
+#endif
+        bool leave = th_t <= 0.9 * theta_entry;
+        if (leave)
+            for (int i = 0; i < nfilt; ++i)
+                if (th_t >= st.filt[2 * i] && ph_t >= st.filt[2 * i + 1]) { leave = false; break; }
+        if (lane == 0) { st.iter += 1; st.state = ST_EVAL; if (leave) st.resto = 0; }
+        W_SYNC();
+        return;
+    }
     if (!accepted) {
         const double an = 0.5 * alpha;
         const bool give_up = !(an >= amin * (1.0 - 1e-12)) || an <= 1e-16;
         if (lane == 0) { st.alpha = an; st.ls_iter += 1; }
         W_SYNC();
-        // No restoration phase.  IPOPT would now minimise the constraint violation; when that cannot be reduced it
-        // returns Infeasible_Problem_Detected (the status the reference loop acts on), so a failed line search away
-        // from feasibility (violation above constr_viol_tol = 1e-4) is reported as 2, otherwise Restoration_Failed.
-        if (give_up) ocp_finish_w(I, S, theta > 1e-4 ? 2 : -2, st.fval);
+        if (give_up) {
+            // IPOPT enters its restoration phase here: it looks for a point whose violation is kappa_resto times the
+            // current one and which the filter, augmented by the current point, accepts; it reports
+            // Infeasible_Problem_Detected (the status the reference loop acts on, MPC_code.py:786) when it ends at a
+            // stationary point of the violation, and Restoration_Failed when called at an (almost) feasible point.
+            // Same entry, goal and exits here; the sub-solver is simpler (proximal Gauss-Newton instead of an l1 IPM).
+            if (theta < 1e-6 || resto_calls >= 3) { ocp_finish_w(I, S, theta > 1e-4 ? 2 : -2, st.fval); return; }
+            if (lane == 0) {
+                if (nfilt < MPCB_MAXFILT) {
+                    st.filt[2 * nfilt] = (1.0 - 1e-5) * theta; st.filt[2 * nfilt + 1] = phi - 1e-8 * theta; st.nfilt = nfilt + 1;
+                }
+                st.resto = 1; st.resto_calls = resto_calls + 1; st.theta_entry = theta; st.state = ST_EVAL;
+            }
+            W_SYNC();
+        }
         return;
     }
     // ---- take the step; bound multipliers with their own step size, then the kappa_sigma safeguard

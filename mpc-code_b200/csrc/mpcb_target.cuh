@@ -163,7 +163,12 @@ MPCB_HD void tgt_eval(const double* w, const double* par, const double* lam, boo
 }
 
 // Whole interior-point solve of one target problem (same algorithm as oracle/ipm.py and mpcb_ocp.cuh).
-MPCB_HD void tgt_solve(const double* par, double* w, double* fout, int* status_out, int* iters_out, const TgtShared& S) {
+// MPCB_TGT_RESTO = false: the regular iterations only; a failed line search returns TGT_NEEDS_RESTO and `tgt_solve`
+// repeats the (cold-started, deterministic) solve with the variant that carries the feasibility restoration.  Keeping
+// the restoration out of the common variant halves its register spills (ptxas: 520 / 1288 B vs 1132 / 1930 B).
+#define TGT_NEEDS_RESTO 1000
+template <bool MPCB_TGT_RESTO>
+MPCB_HD void tgt_solve_t(const double* par, double* w, double* fout, int* status_out, int* iters_out, const TgtShared& S) {
     const IpmOpts& o = S.o;
     const double rf = o.bound_relax;
     double lo[NWS], hi[NWS]; bool hl[NWS], hu[NWS];
@@ -180,6 +185,7 @@ MPCB_HD void tgt_solve(const double* par, double* w, double* fout, int* status_o
     for (int i = 0; i < NWS; ++i) { zL[i] = hl[i] ? 1.0 : 0.0; zU[i] = hu[i] ? 1.0 : 0.0; }
     double mu = o.mu_init, tau = fmax(0.99, 1.0 - mu), dw_last = 0.0, theta0 = -1.0;
     double filt[2 * MPCB_MAXFILT]; int nfilt = 0, acc = 0, it = 0, status = -1;
+    bool resto = false; int resto_calls = 0; double theta_entry = 0.0;      // feasibility restoration, as in ocp_accept
     double f, c[MCS], grad[NWS], J[MCS * NWS], Hp[NWSP];
     tgt_eval(w, par, y, true, &f, c, grad, J, Hp);
     {   // IPOPT: a starting point whose functions do not evaluate ends the solve with Invalid_Number_Detected (-13)
@@ -204,15 +210,17 @@ MPCB_HD void tgt_solve(const double* par, double* w, double* fout, int* status_o
         const double sc = fmax(100.0, zsum / (double)(nb > 0 ? nb : 1)) / 100.0;
         const double E0 = fmax(fmax(dual / sd, prim), c0 / sc);
         if (!(E0 == E0) || !fin(E0)) { status = -13; break; }
-        if (E0 <= o.tol && dual <= 1.0 && prim <= 1e-4 && c0 <= 1e-4) { status = 0; break; }
-        if (E0 <= o.acceptable_tol && dual <= 1e10 && prim <= 1e-2 && c0 <= 1e-2) {
-            if (++acc >= o.acceptable_iter) { status = 1; break; }
-        } else acc = 0;
+        if (!resto) {
+            if (E0 <= o.tol && dual <= 1.0 && prim <= 1e-4 && c0 <= 1e-4) { status = 0; break; }
+            if (E0 <= o.acceptable_tol && dual <= 1e10 && prim <= 1e-2 && c0 <= 1e-2) {
+                if (++acc >= o.acceptable_iter) { status = 1; break; }
+            } else acc = 0;
+        }
         if (it >= o.max_iter) { status = -1; break; }
         // barrier update
         const double mu_min = o.tol / 10.0;
         bool changed = false;
-        while (mu > mu_min) {
+        while (!resto && mu > mu_min) {
             double cm = 0.0;
             for (int j = 0; j < NWS; ++j) {
                 if (hl[j]) cm = fmax(cm, fabs((w[j] - lo[j]) * zL[j] - mu));
@@ -229,10 +237,17 @@ MPCB_HD void tgt_solve(const double* par, double* w, double* fout, int* status_o
         for (int attempt = 0; attempt < 60; ++attempt) {
             for (int i = 0; i < NKS * NKS; ++i) K[i] = 0.0;
             for (int j = 0; j < NWS; ++j) {
-                for (int i = j; i < NWS; ++i) K[i + NKS * j] = Hp[tri(i, j)];
+                for (int i = j; i < NWS; ++i) K[i + NKS * j] = resto ? 0.0 : Hp[tri(i, j)];
                 double sig = dwreg;
-                if (hl[j]) sig += zL[j] / (w[j] - lo[j]);
-                if (hu[j]) sig += zU[j] / (hi[j] - w[j]);
+                if (resto) {             // proximal Gauss-Newton step: zeta D_R^2 + primal barrier Hessian
+                    const double sc = fmax(1.0, fabs(w[j]));
+                    sig += sqrt(mu) / (sc * sc);
+                    if (hl[j]) { const double d = w[j] - lo[j]; sig += mu / (d * d); }
+                    if (hu[j]) { const double d = hi[j] - w[j]; sig += mu / (d * d); }
+                } else {
+                    if (hl[j]) sig += zL[j] / (w[j] - lo[j]);
+                    if (hu[j]) sig += zU[j] / (hi[j] - w[j]);
+                }
                 K[j + NKS * j] += sig;
                 for (int i = 0; i < MCS; ++i) K[NWS + i + NKS * j] = J[i + MCS * j];
             }
@@ -250,6 +265,7 @@ MPCB_HD void tgt_solve(const double* par, double* w, double* fout, int* status_o
         for (int j = 0; j < NWS; ++j) {
             double r = grad[j];
             for (int i = 0; i < MCS; ++i) r += J[i + MCS * j] * y[i];
+            if (resto) r = 0.0;
             if (hl[j]) r -= mu / (w[j] - lo[j]);
             if (hu[j]) r += mu / (hi[j] - w[j]);
             rhs[j] = -r;
@@ -289,6 +305,32 @@ MPCB_HD void tgt_solve(const double* par, double* w, double* fout, int* status_o
         amin *= 0.05;
         double alpha = amax; bool accepted = false, ftype = false;
         double wt[NWS], ft, ct[MCS];
+        if (MPCB_TGT_RESTO && resto) {  // restoration iteration: Armijo on the violation alone
+            double th_t = 0.0;
+            while (alpha > 1e-5) {         // shorter: jammed against the bounds / no descent -> the violation cannot be reduced
+                for (int j = 0; j < NWS; ++j) wt[j] = w[j] + alpha * rhs[j];
+                tgt_eval(wt, par, y, false, &ft, ct, nullptr, nullptr, nullptr);
+                th_t = 0.0;
+                for (int i = 0; i < MCS; ++i) th_t += fabs(ct[i]);
+                if ((th_t == th_t) && fin(th_t) && th_t <= (1.0 - 1e-4 * alpha) * theta) { accepted = true; break; }
+                alpha *= 0.5;
+            }
+            if (!accepted) { status = theta > 1e-4 ? 2 : -2; break; }
+            double b_t = 0.0;
+            for (int j = 0; j < NWS; ++j) {
+                w[j] = wt[j];
+                if (hl[j]) { const double d = w[j] - lo[j]; zL[j] = mu / d; b_t += log(d); }
+                if (hu[j]) { const double d = hi[j] - w[j]; zU[j] = mu / d; b_t += log(d); }
+            }
+            for (int i = 0; i < MCS; ++i) y[i] = 0.0;
+            const double ph_t = ft - mu * b_t;
+            bool leave = th_t <= 0.9 * theta_entry;
+            if (leave) for (int i = 0; i < nfilt; ++i) if (th_t >= filt[2 * i] && ph_t >= filt[2 * i + 1]) { leave = false; break; }
+            if (leave) resto = false;
+            it += 1;
+            tgt_eval(w, par, y, true, &f, c, grad, J, Hp);
+            continue;
+        }
         while (alpha >= amin * (1.0 - 1e-12) && alpha > 1e-16) {
             for (int j = 0; j < NWS; ++j) wt[j] = w[j] + alpha * rhs[j];
             tgt_eval(wt, par, y, false, &ft, ct, nullptr, nullptr, nullptr);
@@ -307,7 +349,13 @@ MPCB_HD void tgt_solve(const double* par, double* w, double* fout, int* status_o
             if (accepted) break;
             alpha *= 0.5;
         }
-        if (!accepted) { status = theta > 1e-4 ? 2 : -2; break; }   // see ocp_accept: no restoration phase
+        if (!accepted) {                // feasibility restoration, same rules as ocp_accept
+            if (theta < 1e-6 || resto_calls >= 3) { status = theta > 1e-4 ? 2 : -2; break; }
+            if (!MPCB_TGT_RESTO) { status = TGT_NEEDS_RESTO; break; }
+            if (nfilt < MPCB_MAXFILT) { filt[2 * nfilt] = (1.0 - 1e-5) * theta; filt[2 * nfilt + 1] = phi - 1e-8 * theta; nfilt++; }
+            resto = true; resto_calls += 1; theta_entry = theta;
+            continue;
+        }
         if (!ftype && nfilt < MPCB_MAXFILT) { filt[2 * nfilt] = (1.0 - 1e-5) * theta; filt[2 * nfilt + 1] = phi - 1e-8 * theta; nfilt++; }
         for (int j = 0; j < NWS; ++j) {
             w[j] = wt[j];
@@ -324,6 +372,27 @@ MPCB_HD void tgt_solve(const double* par, double* w, double* fout, int* status_o
         tgt_eval(w, par, y, false, &f, ct, nullptr, nullptr, nullptr);
     }
     *fout = f; *status_out = status; *iters_out = it;
+}
+
+#ifdef __CUDACC__
+__device__ __noinline__
+#endif
+static void tgt_solve_resto(const double* par, double* w, double* fout, int* status_out, int* iters_out, const TgtShared& S) {
+    tgt_solve_t<true>(par, w, fout, status_out, iters_out, S);
+}
+
+MPCB_HD void tgt_solve(const double* par, double* w, double* fout, int* status_out, int* iters_out, const TgtShared& S) {
+    double w0[NWS];
+    for (int i = 0; i < NWS; ++i) w0[i] = w[i];
+    tgt_solve_t<false>(par, w, fout, status_out, iters_out, S);
+    if (*status_out == TGT_NEEDS_RESTO) {
+        for (int i = 0; i < NWS; ++i) w[i] = w0[i];
+#ifdef __CUDA_ARCH__
+        tgt_solve_resto(par, w, fout, status_out, iters_out, S);
+#else
+        tgt_solve_t<true>(par, w, fout, status_out, iters_out, S);
+#endif
+    }
 }
 #endif  // MPCB_HAS_TARGET
 

@@ -35,8 +35,9 @@ class CompiledProblem:
         self.library = MpcbLibrary(self.build["so"])
         self.flops = self.build["gen"]["flops"]
 
-    def controller(self, batch: int, opts_ss: Optional[Dict] = None, opts_dyn: Optional[Dict] = None, device=None):
-        return BatchedMpc(self, batch, opts_ss, opts_dyn, device)
+    def controller(self, batch: int, opts_ss: Optional[Dict] = None, opts_dyn: Optional[Dict] = None, device=None,
+                   hold_on_failure: bool = False):
+        return BatchedMpc(self, batch, opts_ss, opts_dyn, device, hold_on_failure)
 
 
 def compile_problem(example, name: Optional[str] = None, overrides: Optional[Dict] = None, verbose=False) -> CompiledProblem:
@@ -51,10 +52,18 @@ def compile_problem(example, name: Optional[str] = None, overrides: Optional[Dic
     return CompiledProblem(prob, (name or "problem").lower(), verbose=verbose)
 
 
+def torch_where_failed(t, st, hold):
+    """Status as the warm-start gate sees it: with the hold policy a failed solve counts as infeasible."""
+    return t.where((st < 0) & (st != -13), t.full_like(st, INFEASIBLE), st) if hold else st
+
+
 class BatchedMpc:
     """Loop state of B instances plus the solver objects; ``step()`` is one pass of the hot path."""
 
-    def __init__(self, cp: CompiledProblem, batch: int, opts_ss=None, opts_dyn=None, device=None):
+    def __init__(self, cp: CompiledProblem, batch: int, opts_ss=None, opts_dyn=None, device=None, hold_on_failure: bool = False):
+        """``hold_on_failure``: treat every FAILED OCP solve (iteration limit, restoration failed, ...) like an infeasible
+        one - previous input kept, estimate propagated by the model.  Default False = the reference, which only rejects
+        'Infeasible_Problem_Detected' (``MPC_code.py:786``)."""
         import torch
         self.torch = torch
         self.cp, self.prob, self.B = cp, cp.prob, int(batch)
@@ -63,6 +72,8 @@ class BatchedMpc:
         oss = dict(max_iter=itmax); oss.update(opts_ss or {})
         ody = dict(max_iter=p.sol_optdyn["ipopt.max_iter"]); ody.update(opts_dyn or {})
         self.h = MpcbHandle(cp.library, self.B, oss, ody, device)
+        self.hold_on_failure = bool(hold_on_failure)
+        self.h.set_policy(self.hold_on_failure)
         self.solver_ss = BatchedNlpSolver("target", cp.ss_spec).attach(self.h)
         self.solver = BatchedNlpSolver("ocp", cp.ocp_spec).attach(self.h)
         est = p.estimator
@@ -208,8 +219,11 @@ class BatchedMpc:
             if time_phases:
                 t.cuda.synchronize(dev); out["TIME_DYN"] = time.time() - t0
             st = self.solver.stats()["status"]
-            self.dyn_status = st
-            okd = ((st != INFEASIBLE) & (st != -13)).unsqueeze(1)            # :786-805; a NaN iterate (-13) is never adopted
+            self.dyn_status = torch_where_failed(t, st, self.hold_on_failure)
+            okd = (st != INFEASIBLE) & (st != -13)                           # :786-805; a NaN iterate (-13) is never adopted
+            if self.hold_on_failure:
+                okd = okd & (st >= 0)
+            okd = okd.unsqueeze(1)
             w_new = sol["x"]
             self.w_opt = w_new if self.w_opt is None else t.where(okd, w_new, self.w_opt)
             x_pred = h.model_step(self.xhat_k, self.u_k, self.dhat_k, tt, p_x_k)

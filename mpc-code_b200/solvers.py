@@ -34,7 +34,7 @@ class MpcbOpts(ctypes.Structure):
 C_SYMBOLS = ("mpcb_abi_version", "mpcb_default_opts", "mpcb_get_dims", "mpcb_model_flops", "mpcb_create",
              "mpcb_destroy", "mpcb_last_error", "mpcb_set_const", "mpcb_estimate", "mpcb_target", "mpcb_ocp",
              "mpcb_plant_meas", "mpcb_plant_step", "mpcb_model_output", "mpcb_model_step", "mpcb_stage_derivs",
-             "mpcb_last_launches", "mpcb_last_ticks", "mpcb_total_launches", "mpcb_set_groups", "mpcb_set_profiling", "mpcb_get_profile", "mpcb_dfma_peak",
+             "mpcb_last_launches", "mpcb_last_ticks", "mpcb_total_launches", "mpcb_set_groups", "mpcb_set_policy", "mpcb_set_profiling", "mpcb_get_profile", "mpcb_dfma_peak",
              "mpcb_loop_reset", "mpcb_step", "mpcb_loop_get")
 
 
@@ -67,6 +67,7 @@ class MpcbLibrary:
         L.mpcb_last_launches.argtypes = [vp]; L.mpcb_last_ticks.argtypes = [vp]
         L.mpcb_total_launches.argtypes = [vp]; L.mpcb_total_launches.restype = ctypes.c_long
         L.mpcb_set_groups.argtypes = [vp, ctypes.c_int]
+        L.mpcb_set_policy.argtypes = [vp, ctypes.c_int]
         L.mpcb_set_profiling.argtypes = [vp, ci]
         L.mpcb_get_profile.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_long),
                                        ctypes.POINTER(ctypes.c_ulonglong)]
@@ -257,6 +258,10 @@ class MpcbHandle:
     def set_groups(self, n: int):
         """Cut the batch of the fused step into ``n`` instance groups pipelined on separate streams (`mpcb_set_groups`)."""
         self._check(self.L.mpcb_set_groups(self._h, int(n)))
+
+    def set_policy(self, hold_failed: bool):
+        """Fused step: hold the previous input on every failed solve instead of applying its iterate (`mpcb_set_policy`)."""
+        self._check(self.L.mpcb_set_policy(self._h, 1 if hold_failed else 0))
 
     def loop_state(self):
         """Copies of the device-resident loop state: xi = [x(k+1|k); d], P, u."""

@@ -16,7 +16,7 @@ reference and cannot be installed here, so this follows its published algorithm
   dual_inf_tol 1, constr_viol_tol 1e-4, compl_inf_tol 1e-4; "acceptable" exit after 15
   consecutive iterations at 1e-6;
 * filter line search (gamma_theta 1e-5, gamma_phi 1e-8, eta_phi 1e-8, s_theta 1.1, s_phi 2.3,
-  delta 1) with backtracking by 1/2; no second-order correction, no watchdog and no restoration
+  delta 1) with backtracking by 1/2; no second-order correction, no watchdog; restoration by proximal Gauss-Newton
   phase: a failed line search ends with ``Infeasible_Problem_Detected`` when the constraint
   violation is above ``constr_viol_tol`` (what IPOPT's restoration reports when it cannot reduce
   it) and with ``Restoration_Failed`` otherwise;
@@ -78,6 +78,11 @@ class IpmOptions:
     delta_c_bar: float = 1e-8
     kappa_c: float = 0.25
     hessian_constant: bool = False
+    # feasibility restoration (entered when the filter line search fails; see `solve_nlp`)
+    resto_kappa: float = 0.9            # required reduction of the violation (IPOPT required_infeasibility_reduction)
+    resto_max_calls: int = 3
+    resto_armijo: float = 1e-4
+    resto_alpha_min: float = 1e-5
     verbose: bool = False
 
 
@@ -222,6 +227,7 @@ def solve_nlp(n: int, m: int, fun: Callable, x0, xL, xU, gL, gU, opts: Optional[
     theta0 = None
     status = -1
     it = 0
+    resto, resto_calls, theta_entry = False, 0, 0.0
     ev = evaluate(v, y, 2)
     info: Dict[str, float] = {}
 
@@ -243,10 +249,12 @@ def solve_nlp(n: int, m: int, fun: Callable, x0, xL, xU, gL, gU, opts: Optional[
         if not np.isfinite(E0):
             status = -13
             break
-        if E0 <= o.tol and dual0 <= o.dual_inf_tol and prim0 <= o.constr_viol_tol and comp0 <= o.compl_inf_tol:
+        if not resto and E0 <= o.tol and dual0 <= o.dual_inf_tol and prim0 <= o.constr_viol_tol and comp0 <= o.compl_inf_tol:
             status = 0
             break
-        if (E0 <= o.acceptable_tol and dual0 <= o.acceptable_dual_inf_tol and prim0 <= o.acceptable_constr_viol_tol
+        if resto:
+            pass
+        elif (E0 <= o.acceptable_tol and dual0 <= o.acceptable_dual_inf_tol and prim0 <= o.acceptable_constr_viol_tol
                 and comp0 <= o.acceptable_compl_inf_tol):
             acceptable_count += 1
             if acceptable_count >= o.acceptable_iter:
@@ -260,7 +268,7 @@ def solve_nlp(n: int, m: int, fun: Callable, x0, xL, xU, gL, gU, opts: Optional[
         # barrier parameter update
         mu_min = o.tol / 10.0
         changed = False
-        while mu > mu_min and errors(ev, v, y, zL, zU, mu)[0] <= o.kappa_eps * mu:
+        while not resto and mu > mu_min and errors(ev, v, y, zL, zU, mu)[0] <= o.kappa_eps * mu:
             mu = max(mu_min, min(o.kappa_mu * mu, mu ** o.theta_mu))
             tau = max(o.tau_min, 1.0 - mu)
             changed = True
@@ -271,6 +279,14 @@ def solve_nlp(n: int, m: int, fun: Callable, x0, xL, xU, gL, gU, opts: Optional[
         sigma = np.where(hasL, zL / dL, 0.0) + np.where(hasU, zU / dU, 0.0)
         J, W = ev["J"], ev["W"]
         r1 = ev["grad"] + J.T @ y - np.where(hasL, mu / dL, 0.0) + np.where(hasU, mu / dU, 0.0)
+        if resto:
+            # Feasibility restoration step (proximal Gauss-Newton on the constraint violation): minimise
+            #   zeta/2 |D_R dv|^2 - mu sum log(slacks to the bounds)   s.t.   C + J dv = 0,
+            # zeta = sqrt(mu), D_R = diag(1 / max(1, |v|)) - IPOPT's restoration objective with the reference point reset
+            # to the current iterate every iteration, the l1 penalty replaced by the linearised constraints.
+            sigma = np.where(hasL, mu / dL ** 2, 0.0) + np.where(hasU, mu / dU ** 2, 0.0)
+            W = np.diag(np.sqrt(mu) / np.maximum(1.0, np.abs(v)) ** 2)
+            r1 = -np.where(hasL, mu / dL, 0.0) + np.where(hasU, mu / dU, 0.0)
         rhs = -np.concatenate([r1, ev["C"]])
         K0 = np.zeros((nv + mc, nv + mc))
         K0[:nv, :nv] = W + np.diag(sigma)
@@ -334,6 +350,34 @@ def solve_nlp(n: int, m: int, fun: Callable, x0, xL, xU, gL, gU, opts: Optional[
         accepted = False
         ftype = False
         ev_t = None
+        if resto:
+            # restoration iteration: Armijo backtracking on the violation alone.  A step shorter than resto_alpha_min of
+            # the Gauss-Newton step (jammed against the bounds, or no descent) means the violation cannot be reduced.
+            while alpha > o.resto_alpha_min:
+                vt = v + alpha * dv
+                ev_t = evaluate(vt, y, 0)
+                th_t = np.abs(ev_t["C"]).sum()
+                if np.isfinite(th_t) and th_t <= (1.0 - o.resto_armijo * alpha) * theta:
+                    accepted = True
+                    break
+                alpha *= 0.5
+            if o.verbose:
+                print("it %3d RESTO mu %.1e theta %.3e -> %.3e (entry %.3e) amax %.2e alpha %.2e %s" % (
+                    it, mu, theta, th_t, theta_entry, alpha_max, alpha, "acc" if accepted else "REJ"))
+            if not accepted:             # the violation cannot be reduced: a stationary point of the infeasibility
+                status = 2 if theta > o.constr_viol_tol else -2
+                break
+            v = vt
+            it += 1
+            # multipliers are not iterated during restoration; they restart from zero / mu over the slack
+            y = np.zeros(mc)
+            dLn = np.where(hasL, v - lo, 1.0); dUn = np.where(hasU, hi - v, 1.0)
+            zL = np.where(hasL, mu / dLn, 0.0); zU = np.where(hasU, mu / dUn, 0.0)
+            ph_t = barrier(ev_t["f"], v)
+            if th_t <= o.resto_kappa * theta_entry and not any(th_t >= tf_ and ph_t >= pf_ for tf_, pf_ in filt):
+                resto = False            # sufficiently more feasible and acceptable to the filter: resume
+            ev = evaluate(v, y, 2)
+            continue
         while alpha >= a_min * (1 - 1e-12) and alpha > 1e-16:
             vt = v + alpha * dv
             ev_t = evaluate(vt, y, 0)
@@ -364,11 +408,18 @@ def solve_nlp(n: int, m: int, fun: Callable, x0, xL, xU, gL, gU, opts: Optional[
             print("it %3d mu %.1e E0 %.2e theta %.3e phi %.8e gphid %.2e amax %.2e az %.2e alpha %.2e dw %.1e %s nfilt %d a_min %.1e"
                   % (it, mu, E0, theta, phi, gphi_d, alpha_max, alpha_z, alpha, delta_w, "acc" if accepted else "REJ", len(filt), a_min))
         if not accepted:
-            # IPOPT would enter its restoration phase here.  It is not restated; what it reports when the violation
-            # cannot be reduced - Infeasible_Problem_Detected - is returned whenever the line search fails away from
-            # feasibility (violation above constr_viol_tol), otherwise Restoration_Failed.
-            status = 2 if theta > o.constr_viol_tol else -2
-            break
+            # IPOPT enters its restoration phase here: it looks for a point with a violation reduced to kappa_resto
+            # times the current one that the filter (augmented by the current point) accepts, and reports
+            # Infeasible_Problem_Detected when it ends at a stationary point of the violation instead.  Restated with a
+            # simpler sub-solver (proximal Gauss-Newton steps, above) but the same entry, goal and exits.  Called at an
+            # (almost) feasible point, or too often, it gives up as IPOPT does: Restoration_Failed.
+            if theta < 1e-2 * o.constr_viol_tol or resto_calls >= o.resto_max_calls:
+                status = 2 if theta > o.constr_viol_tol else -2
+                break
+            filt.append(((1 - o.gamma_theta) * theta, phi - o.gamma_phi * theta))
+            resto, theta_entry = True, theta
+            resto_calls += 1
+            continue
         if not ftype:
             filt.append(((1 - o.gamma_theta) * theta, phi - o.gamma_phi * theta))
         v = v + alpha * dv

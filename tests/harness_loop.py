@@ -29,13 +29,13 @@ class HarnessLoop:
         p_ymp = get("def_pymp", p.npyp) if "def_pymp" in ns else (p_yk[:, 0].copy() if "def_py" in ns else np.zeros(p.npyp))
         return p_xk, p_yk, p_xmp, p_ymp, get("def_pxp", p.npxp), get("def_pyp", p.npyp)
 
-    def run(self, Nsim, x0=None, noise=None):
+    def run(self, Nsim, x0=None, noise=None, x0_m=None):
         b, B, H = self.b, self.B, self.H
         p = b.prob
         nx, nu, ny, nd, N = p.nx, p.nu, p.ny, p.nd, p.N
         nxu = nx + nu
         x_k = np.ascontiguousarray(np.tile(p.x0_p, (B, 1)) if x0 is None else x0, dtype=float).copy()
-        x0_m = np.ascontiguousarray(np.tile(p.x0_m, (B, 1)) if x0 is None else x0, dtype=float).copy()
+        x0_m = np.ascontiguousarray(np.tile(p.x0_m, (B, 1)) if x0 is None else (x0 if x0_m is None else x0_m), dtype=float).copy()
         u_k = np.tile(p.u0, (B, 1)); xhat = x0_m.copy(); dhat = np.tile(p.dhat0, (B, 1))
         est = p.estimator
         est_type = 0 if est["type"] == "kalss" else 1

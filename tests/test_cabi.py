@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol(nmpc):
 def test_dims_and_flop_table_are_reported(nmpc):
     L = MpcbLibrary(nmpc.lib["so"])
     d, p = L.dims, nmpc.prob
-    assert L.lib.mpcb_abi_version() == 1
+    assert L.lib.mpcb_abi_version() == 2
     assert (d.nx, d.nu, d.ny, d.nd, d.N, d.Mx) == (p.nx, p.nu, p.ny, p.nd, p.N, 10)
     assert (d.nw, d.npar, d.ng, d.nwss, d.nparss, d.nxi) == (p.nw, p.npar, p.ny, p.nx + p.nu + p.ny, p.npar_ss, p.nxi)
     assert d.has_ocp == 1 and d.has_target == 1

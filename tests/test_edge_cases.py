@@ -83,3 +83,51 @@ def test_gpu_single_instance_and_iteration_limit(nmpc):
         r = on.solve(nmpc.cold_guess(), par, lb, ub, opts=IpmOptions(max_iter=max_iter))
         assert int(solver.stats()["status"][0]) == status == r.status
         assert np.abs(sol["x"].cpu().numpy()[0] - r.x).max() < 1e-6
+
+
+def _enmpc_hard_start(enmpc):
+    """Cold-started first OCP of Ex_ENMPC from the plant state of instance 3677 of the full-batch workload: the filter
+    line search fails at iteration 12 (step limited to 3e-3 with the violation growing along it) - the restoration case."""
+    p = enmpc.prob
+    eps = np.random.default_rng(20240419 + 3677).uniform(-1, 1, p.nxp)
+    return np.clip(np.array([0.9, 0.1]) + 0.05 * eps, 0.0, 1.0)
+
+
+def test_failed_line_search_is_recovered_by_the_feasibility_restoration(enmpc):
+    from harness_loop import HarnessLoop
+    from oracle.closed_loop import OracleLoop
+    x0 = _enmpc_hard_start(enmpc)
+    p = enmpc.prob
+    ref = OracleLoop(p, enmpc.ss, enmpc.ocp, enmpc.oracle).run(Nsim=2, x0_p=x0, x0_m=p.x0_m)
+    rec = HarnessLoop(enmpc, 1).run(2, x0=x0[None, :], x0_m=p.x0_m[None, :])
+    assert ref["STATUS_DYN"].tolist() == [0, 0] and rec["STATUS_DYN"][:, 0].tolist() == [0, 0]
+    assert ref["ITER_DYN"][0] == rec["ITER_DYN"][0, 0] == 26          # 12 regular + 1 restoration + 13 regular iterations
+    assert np.abs(rec["U"][:, 0, :] - ref["U"]).max() < 1e-6
+
+
+@pytest.mark.gpu
+def test_gpu_restoration_and_failure_policy(enmpc, nmpc):
+    """(1) the restoration case on the device: same status / iterations / input as the oracle; (2) the hold policy: with
+    an iteration limit of 3 every solve fails (-1): the reference applies those iterates, the hold policy keeps u0."""
+    import torch
+    from mpc_code_b200.mpc_loop import CompiledProblem
+    from oracle.closed_loop import OracleLoop
+    x0 = _enmpc_hard_start(enmpc)
+    p = enmpc.prob
+    ref = OracleLoop(p, enmpc.ss, enmpc.ocp, enmpc.oracle).run(Nsim=2, x0_p=x0, x0_m=p.x0_m)
+    ctl = CompiledProblem(p, "enmpc_reactor").controller(4)
+    ctl.reset(x0_p=np.tile(x0, (4, 1)), x0_m=np.tile(p.x0_m, (4, 1)))
+    rec = ctl.run(2, fused=True)
+    assert rec["STATUS_DYN"].cpu().numpy().tolist() == [[0] * 4] * 2
+    assert rec["ITER_DYN"].cpu().numpy()[0].tolist() == [int(ref["ITER_DYN"][0])] * 4
+    assert np.abs(rec["U"].cpu().numpy()[:, 0, :] - ref["U"]).max() < 1e-6
+    pn = nmpc.prob
+    cpn = CompiledProblem(pn, "nmpc_cstr")
+    x0n = pn.x0_p * (1 + np.array([0.01, 0.001, 0.01]))
+    for hold, fused in ((False, True), (True, True), (True, False)):
+        c = cpn.controller(3, opts_dyn=dict(max_iter=3), hold_on_failure=hold)
+        c.reset(x0_p=np.tile(x0n, (3, 1)), x0_m=np.tile(x0n, (3, 1)))
+        r = c.run(2, fused=fused)
+        assert (r["STATUS_DYN"] == -1).all()
+        moved = (r["U"] - torch.as_tensor(pn.u0, device=r["U"].device)).abs().max().item() > 1e-9
+        assert moved != hold

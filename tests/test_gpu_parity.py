@@ -256,11 +256,10 @@ def test_enmpc_full_batch(enmpc):
     ctl.reset(x0_p=x0, x0_m=np.tile(p.x0_m, (B, 1)))
     rec = ctl.run(p.Nsim, fused=True)
     st = rec["STATUS_DYN"].cpu().numpy()
-    # The cold-started first OCP (27 iterations on average) is hard: for 1 of these 4 096 starts the line search fails
-    # at a nearly singular point (step length limited to 3e-3, violation growing along the step).  IPOPT would enter its
-    # restoration phase there, which is not implemented: the solve reports Infeasible_Problem_Detected and the loop keeps
-    # the previous input (MPC_code.py:786-805).  Everything after the first step must succeed.
-    assert np.isin(st, (0, 2)).all() and (st[0] == 2).sum() <= 4 and (st[1:] == 0).all(), np.unique(st, return_counts=True)
+    # The cold-started first OCP (27 iterations on average) is hard: for 1 of these 4 096 starts (instance 3677) the line
+    # search fails at a nearly singular point (step length limited to 3e-3, violation growing along the step) and the
+    # feasibility restoration takes over for one iteration (tests/test_edge_cases.py checks that solve against the oracle).
+    assert (st == 0).all(), np.unique(st, return_counts=True)
     u = rec["U"].cpu().numpy()
     lo, hi = enmpc.ocp.bounds["umin"], enmpc.ocp.bounds["umax"]
     assert np.all(u >= lo - 1e-7 * np.maximum(1, np.abs(lo))) and np.all(u <= hi + 1e-7 * np.maximum(1, np.abs(hi)))
