@@ -89,7 +89,7 @@ __global__ void EVAL_BOUNDS k_ocp_eval(OcpArgs a) {
 #if MPCB_KKT_LANES > 1
 __global__ void __launch_bounds__(32 * KKT_WARPS) k_ocp_kkt(OcpArgs a) {
     constexpr int GROUPS = 32 * KKT_WARPS / MPCB_KKT_LANES;        // instances per block
-    __shared__ double scratch[GROUPS][KktScratch::total];
+    __shared__ __align__(16) double scratch[GROUPS][KktScratch::total];
     const int inst = (blockIdx.x * blockDim.x + threadIdx.x) / MPCB_KKT_LANES;
     if (inst >= a.B) return;
     if (a.st[inst].state != ST_EVAL) return;

@@ -198,11 +198,11 @@ MPCB_HD double push_in(double v, double lo, double hi, double kappa) {
 }
 
 MPCB_HD void stage_params(const double* par, int k, double* d, double* px, double* py, double* t0) {
-#pragma unroll
+MPCB_UNROLL
     for (int i = 0; i < ND; ++i) d[i] = par[MPCB_OFF_D + i];
-#pragma unroll
+MPCB_UNROLL
     for (int i = 0; i < NPX; ++i) px[i] = par[MPCB_OFF_PX + k * NPX + i];
-#pragma unroll
+MPCB_UNROLL
     for (int i = 0; i < NPY; ++i) py[i] = par[MPCB_OFF_PY + k * NPY + i];
     *t0 = par[MPCB_OFF_T];
 }
@@ -252,7 +252,7 @@ MPCB_HD void ocp_init_stage(OcpInst& I, const OcpShared& S, int k) {
             I.zL[wi] = fin(S.lbx[wi]) ? 1.0 : 0.0;
             I.zU[wi] = fin(S.ubx[wi]) ? 1.0 : 0.0;
         }
-#pragma unroll
+MPCB_UNROLL
         for (int i = 0; i < NXA; ++i) I.lam[k * NXA + i] = 0.0;
 #if NG > 0
         double d[ND + 1], px[NPX + 1], py[NPY + 1], t0, Y[NG];
@@ -308,9 +308,9 @@ MPCB_HD void ocp_eval_stage(OcpInst& I, const OcpShared& S, int k, RkBuf rb = Rk
     const double* w = I.w;
     const double rf = S.o.bound_relax;
     double z[NXA], u[NU], lam[NXA], d[ND + 1], px[NPX + 1], py[NPY + 1], t0;
-#pragma unroll
+MPCB_UNROLL
     for (int i = 0; i < NXA; ++i) { z[i] = w[k * NZA + i]; lam[i] = I.lam[k * NXA + i]; }
-#pragma unroll
+MPCB_UNROLL
     for (int i = 0; i < NU; ++i) u[i] = w[k * NZA + NXA + i];
     stage_params(I.par, k, d, px, py, &t0);
     double xn[NXA], A[NXA * NXA], Bm[NXA * NU], Hp[NZAP], l, g[NZA];
@@ -320,10 +320,10 @@ MPCB_HD void ocp_eval_stage(OcpInst& I, const OcpShared& S, int k, RkBuf rb = Rk
         constexpr int NS = NX + 1, NZS = NS + NU;
         ContCtx cc; cc.u = u; cc.par = I.par; cc.pxk = px; cc.pyk = py;
         double xt[NS], lt[NS], xe[NS], S[NS * NZS], Ht[NZS * (NZS + 1) / 2];
-#pragma unroll
+MPCB_UNROLL
         for (int i = 0; i < NX; ++i) { xt[i] = z[i]; lt[i] = lam[i]; }
         xt[NX] = 0.0; lt[NX] = 1.0;
-#pragma unroll
+MPCB_UNROLL
         for (int i = 0; i < NZS * (NZS + 1) / 2; ++i) Ht[i] = 0.0;
         if constexpr (EXT) {
             rk4_full_t<SysCont>(xt, cc, t0, lt, xe, S, Ht, rb);
@@ -332,16 +332,16 @@ MPCB_HD void ocp_eval_stage(OcpInst& I, const OcpShared& S, int k, RkBuf rb = Rk
             rk4_full_t<SysCont>(xt, cc, t0, lt, xe, S, Ht, RkBuf{lbuf, 1});
         }
         l = xe[NX];
-#pragma unroll
+MPCB_UNROLL
         for (int j = 0; j < NZ; ++j) {
             const int js = (j < NX) ? j : j + 1;          // skip the q0 column
             g[j] = S[NX + NS * js];
-#pragma unroll
+MPCB_UNROLL
             for (int i = 0; i < NX; ++i) { if (j < NX) A[i + NX * j] = S[i + NS * js]; else Bm[i + NX * (j - NX)] = S[i + NS * js]; }
-#pragma unroll
+MPCB_UNROLL
             for (int i = 0; i <= j; ++i) { const int is = (i < NX) ? i : i + 1; Hp[tri(j, i)] += Ht[tri(js, is)]; }
         }
-#pragma unroll
+MPCB_UNROLL
         for (int i = 0; i < NX; ++i) xn[i] = xe[i];
     }
 #elif NAUG == 0
@@ -349,31 +349,31 @@ MPCB_HD void ocp_eval_stage(OcpInst& I, const OcpShared& S, int k, RkBuf rb = Rk
 #else
     {   // model part by the RK4 sweeps, then embedded into the augmented stage:  z+ = [Fx(x,u); u]
         double xm[NX], Am[NX * NX], Bmm[NX * NU], Hm[NZP];
-#pragma unroll
+MPCB_UNROLL
         for (int i = 0; i < NZP; ++i) Hm[i] = 0.0;
         dyn_full<EXT>(z, u, d, px, t0, lam, xm, Am, Bmm, Hm, rb);
-#pragma unroll
+MPCB_UNROLL
         for (int i = 0; i < NXA * NXA; ++i) A[i] = 0.0;
-#pragma unroll
+MPCB_UNROLL
         for (int i = 0; i < NXA * NU; ++i) Bm[i] = 0.0;
-#pragma unroll
+MPCB_UNROLL
         for (int j = 0; j < NX; ++j)
-#pragma unroll
+MPCB_UNROLL
             for (int i = 0; i < NX; ++i) A[i + NXA * j] = Am[i + NX * j];
-#pragma unroll
+MPCB_UNROLL
         for (int j = 0; j < NU; ++j) {
-#pragma unroll
+MPCB_UNROLL
             for (int i = 0; i < NX; ++i) Bm[i + NXA * j] = Bmm[i + NX * j];
             Bm[NX + j + NXA * j] = 1.0;
         }
-#pragma unroll
+MPCB_UNROLL
         for (int i = 0; i < NX; ++i) xn[i] = xm[i];
-#pragma unroll
+MPCB_UNROLL
         for (int i = 0; i < NU; ++i) xn[NX + i] = u[i];
         // model Hessian (ordering x,u) into the augmented ordering (x, v, u)
-#pragma unroll
+MPCB_UNROLL
         for (int i = 0; i < NZ; ++i)
-#pragma unroll
+MPCB_UNROLL
             for (int j = 0; j <= i; ++j) {
                 const int ia = (i < NX) ? i : i + NAUG, ja = (j < NX) ? j : j + NAUG;
                 Hp[tri(ia, ja)] += Hm[tri(i, j)];
@@ -394,9 +394,9 @@ MPCB_HD void ocp_eval_stage(OcpInst& I, const OcpShared& S, int k, RkBuf rb = Rk
     const bool resto = I.st->resto != 0;
     const double rmu = resto ? I.st->mu : 0.0, zeta = resto ? sqrt(I.st->mu) : 0.0;
     if (resto) {
-#pragma unroll
+MPCB_UNROLL
         for (int i = 0; i < NZAP; ++i) Hp[i] = 0.0;
-#pragma unroll
+MPCB_UNROLL
         for (int j = 0; j < NZA; ++j) {
             const double vj = w[k * NZA + j], sc = fmax(1.0, fabs(vj));
             Hp[tri(j, j)] = zeta / (sc * sc);
@@ -405,7 +405,7 @@ MPCB_HD void ocp_eval_stage(OcpInst& I, const OcpShared& S, int k, RkBuf rb = Rk
     }
     double th = 0.0, prim = 0.0, ysum = 0.0, zsum = 0.0, nb = 0.0, pmin = 1e300, pmax = -1e300;
     double prod = 1.0;     // product of all slacks-to-bounds of the stage: one log instead of one per bound
-#pragma unroll
+MPCB_UNROLL
     for (int i = 0; i < NXA; ++i) {
         const double ci = xn[i] - w[(k + 1) * NZA + i];
         r[R_C + i] = ci;
@@ -413,15 +413,15 @@ MPCB_HD void ocp_eval_stage(OcpInst& I, const OcpShared& S, int k, RkBuf rb = Rk
     }
     // dual residual of the stage variables, started with the cost gradient and the dynamics multipliers
     double res[NZA], dg[NZA];
-#pragma unroll
+MPCB_UNROLL
     for (int j = 0; j < NZA; ++j) {
         double a = g[j];
-#pragma unroll
+MPCB_UNROLL
         for (int i = 0; i < NXA; ++i) a += ((j < NXA) ? A[i + NXA * j] : Bm[i + NXA * (j - NXA)]) * lam[i];
         if (j < NXA && k > 0) a -= I.lam[(k - 1) * NXA + j];
         res[j] = a; dg[j] = 0.0;
     }
-#pragma unroll
+MPCB_UNROLL
     for (int j = 0; j < NZA; ++j) {
         const int wi = k * NZA + j;
         const bool active = !(k == 0 && j < NXA);          // x_0 is fixed
@@ -431,25 +431,25 @@ MPCB_HD void ocp_eval_stage(OcpInst& I, const OcpShared& S, int k, RkBuf rb = Rk
         res[j] += zU - zL;
     }
     double M[NZA * NZA], dual_s = 0.0;
-#pragma unroll
+MPCB_UNROLL
     for (int j = 0; j < NZA; ++j)
-#pragma unroll
+MPCB_UNROLL
         for (int i = 0; i < NZA; ++i) M[i + NZA * j] = Hp[tri(i, j)] + (i == j ? dg[j] : 0.0);
 #if NG > 0
     {
         double Y[NG], JY[NG * NZA], HY[NZAP], mult[NG];
-#pragma unroll
+MPCB_UNROLL
         for (int i = 0; i < NG; ++i) mult[i] = I.ym[k * NG + i];
         ocp_out_d(z, u, I.par, px, py, mult, Y, JY, HY);
 #if !MPCB_OUT_LINEAR
         if (!resto) {
-#pragma unroll
+MPCB_UNROLL
             for (int j = 0; j < NZA; ++j)
-#pragma unroll
+MPCB_UNROLL
                 for (int i = 0; i < NZA; ++i) M[i + NZA * j] += HY[tri(i, j)];
         }
 #endif
-#pragma unroll
+MPCB_UNROLL
         for (int q = 0; q < NG; ++q) {
             const int gi = k * NG + q;
             const double sv = I.s[gi], lo = S.lbg[gi], hi = S.ubg[gi];
@@ -462,24 +462,24 @@ MPCB_HD void ocp_eval_stage(OcpInst& I, const OcpShared& S, int k, RkBuf rb = Rk
             r[R_RG + q] = rg; r[R_YM + q] = mult[q]; r[R_GV + q] = Y[q];
             th += fabs(rg); prim = fmax(prim, fabs(rg)); ysum += fabs(mult[q]);
             dual_s = fmax(dual_s, fabs(-mult[q] - vl + vu));   // dual residual of the slack
-#pragma unroll
+MPCB_UNROLL
             for (int j = 0; j < NZA; ++j) {
                 r[R_G + q + NG * j] = JY[q + NG * j];
                 res[j] += JY[q + NG * j] * mult[q];
-#pragma unroll
+MPCB_UNROLL
                 for (int i = 0; i < NZA; ++i) M[i + NZA * j] += JY[q + NG * i] * sig * JY[q + NG * j];
             }
         }
     }
 #endif
     double dual = dual_s;
-#pragma unroll
+MPCB_UNROLL
     for (int j = 0; j < NZA; ++j) if (!(k == 0 && j < NXA)) dual = fmax(dual, fabs(res[j]));
-#pragma unroll
+MPCB_UNROLL
     for (int i = 0; i < NXA * NXA; ++i) r[R_AB + i] = A[i];
-#pragma unroll
+MPCB_UNROLL
     for (int i = 0; i < NXA * NU; ++i) r[R_AB + NXA * NXA + i] = Bm[i];
-#pragma unroll
+MPCB_UNROLL
     for (int i = 0; i < NZA * NZA; ++i) r[R_M + i] = M[i];
     r[R_PART + 0] = l; r[R_PART + 1] = th; r[R_PART + 2] = dual; r[R_PART + 3] = prim; r[R_PART + 4] = ysum;
     r[R_PART + 5] = zsum; r[R_PART + 6] = nb; r[R_PART + 7] = pmin; r[R_PART + 8] = pmax; r[R_PART + 9] = log(prod);
@@ -487,7 +487,7 @@ MPCB_HD void ocp_eval_stage(OcpInst& I, const OcpShared& S, int k, RkBuf rb = Rk
     {
         double* rg_ = I.rec + k * REC_SZ;               // 16-byte aligned: REC_SZ and the workspace offsets are even
 #ifdef __CUDA_ARCH__
-#pragma unroll
+MPCB_UNROLL
         for (int i = 0; i < (R_PART + NPART + 1) / 2; ++i)
             reinterpret_cast<double2*>(rg_)[i] = make_double2(r[2 * i], (2 * i + 1 < R_PART + NPART) ? r[2 * i + 1] : 0.0);
 #else
@@ -500,7 +500,7 @@ MPCB_HD void ocp_eval_stage(OcpInst& I, const OcpShared& S, int k, RkBuf rb = Rk
         double* t = I.trec;
         ocp_term_d(w + NH * NZA, I.par, &V, gN, HN);           // terminal cost acts on x_N only (Control_Calc.py:194-196,209)
         double dualN = 0.0, zs = 0.0, nbn = 0.0, pmn = 1e300, pmx = -1e300, prodN = 1.0;
-#pragma unroll
+MPCB_UNROLL
         for (int j = 0; j < NXA; ++j) {
             const int wi = NH * NZA + j;
             double iL, iU, zL, zU, qL, qU, sig = 0.0;
@@ -512,7 +512,7 @@ MPCB_HD void ocp_eval_stage(OcpInst& I, const OcpShared& S, int k, RkBuf rb = Rk
             if (j < NX) dr += I.nuT[j];
 #endif
             dualN = fmax(dualN, fabs(dr));
-#pragma unroll
+MPCB_UNROLL
             for (int i = 0; i < NXA; ++i) {
                 double hij = (i < NX && j < NX) ? HN[tri(i, j)] : 0.0;
                 if (resto) { const double sc = fmax(1.0, fabs(w[wi])); hij = (i == j) ? zeta / (sc * sc) : 0.0; }
@@ -568,9 +568,19 @@ MPCB_HD void ocp_eval_stage(OcpInst& I, const OcpShared& S, int k, RkBuf rb = Rk
 #define KKT_STAGED (MPCB_KKT_LANES > 1)        // records staged through the scratch (lane mappings) or read in place
 
 // scratch (doubles): shared memory per warp with 32 lanes, thread-local (registers) with one lane
+// Record streaming of the lane mappings on the device: bulk asynchronous copies (cp.async.bulk, the TMA engine; SASS
+// UBLKCP) from the workspace straight into a ring of KKT_NBUF shared-memory buffers, completion signalled on one mbarrier
+// per buffer, issued KKT_NBUF - 1 stages ahead of the stage being processed.  Round 1 staged the next record through
+// registers (one stage ahead): a third of the kernel's stall samples sat on that copy (profiles/r02_v2_sass_k_ocp_kkt.txt).
+#ifndef MPCB_KKT_TMA
+#define MPCB_KKT_TMA 1
+#endif
+#define KKT_RBUF ((R_BWD + 1) / 2 * 2)          // doubles per ring buffer: a 16-byte multiple
+#define KKT_NBUF (KKT_RBUF > 600 ? 2 : 3)       // large stage blocks: two buffers (the scratch must fit 48 kB of static shared memory)
 struct KktScratch {
-    static constexpr int R = 0;                                     // staged record (32-lane mapping only)
-    static constexpr int P = R + (KKT_STAGED ? (R_BWD + 1) / 2 * 2 : 0);   // NXA x NXA  cost-to-go Hessian of the next stage
+    static constexpr int R = 0;                                     // staged records (lane mappings only): KKT_NBUF buffers
+    static constexpr int BAR = R + (KKT_STAGED ? KKT_NBUF * KKT_RBUF : 0);   // KKT_NBUF mbarriers (8 bytes each)
+    static constexpr int P = BAR + (KKT_STAGED ? (KKT_NBUF + 1) / 2 * 2 : 0);   // NXA x NXA  cost-to-go Hessian of the next stage
     static constexpr int p = P + NXA * NXA;             // NXA
     static constexpr int M = p + NXA;                  // NZA x NZA  condensed stage Hessian
     static constexpr int q = M + NZA * NZA;             // NZA
@@ -591,8 +601,53 @@ struct KktScratch {
     static constexpr int Gm = Ga + NU * NXT;          // NXT x NXT
     static constexpr int hT = Gm + NXT * NXT;         // NXT
     static constexpr int nuS = hT + NXT;              // NXT
-    static constexpr int total = nuS + NXT;
+    static constexpr int total = (nuS + NXT + 1) / 2 * 2;           // even: every instance's scratch stays 16-byte aligned
 };
+
+#if defined(__CUDA_ARCH__) && KKT_STAGED && MPCB_KKT_TMA
+#define KKT_USE_TMA 1
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(void* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, void* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void* bar, unsigned parity) {
+    asm volatile("{\n .reg .pred p;\n WAIT_LOOP:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra WAIT_DONE;\n"
+                 " bra WAIT_LOOP;\n WAIT_DONE:\n }" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// Ring of record buffers of one instance (one lane group).  `phase` holds the parity of every buffer's next completion.
+struct RecRing {
+    double* buf; unsigned long long* bar; unsigned phase;
+    __device__ __forceinline__ void init(double* sm, int lane) {
+        buf = sm + KktScratch::R; bar = reinterpret_cast<unsigned long long*>(sm + KktScratch::BAR); phase = 0u;
+        if (lane == 0) {
+            for (int b = 0; b < KKT_NBUF; ++b) mbar_init(bar + b, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+    }
+    // queue the copy of n0 doubles from g0 (and n1 from g1, placed after the first n0) into buffer b; one lane calls it
+    __device__ __forceinline__ void issue(int b, const double* g0, int n0, const double* g1, int n1) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // earlier reads of this buffer precede the overwrite
+        mbar_expect_tx(bar + b, 8u * (unsigned)(n0 + n1));
+        bulk_g2s(buf + b * KKT_RBUF, g0, 8u * (unsigned)n0, bar + b);
+        if (n1 > 0) bulk_g2s(buf + b * KKT_RBUF + n0, g1, 8u * (unsigned)n1, bar + b);
+    }
+    // every lane: wait for buffer b
+    __device__ __forceinline__ const double* wait(int b) {
+        mbar_wait(bar + b, (phase >> b) & 1u);
+        phase ^= 1u << b;
+        return buf + b * KKT_RBUF;
+    }
+};
+#else
+#define KKT_USE_TMA 0
+#endif
 
 // Streaming of the per-stage records by the sequential sweeps.  With 32 lanes the record of the NEXT stage to be
 // visited is loaded into registers (REC_PER_LANE doubles per lane) while the current stage is being processed, and
@@ -605,7 +660,7 @@ struct RecStream {
 };
 MPCB_HD void rec_prefetch(RecStream& rs, const double* rk) {
 #if KKT_ON_LANES
-#pragma unroll
+MPCB_UNROLL
     for (int q = 0; q < REC_PER_LANE; ++q) { const int e = LANE_ID + N_LANES * q; rs.pre[q] = (e < R_BWD) ? rk[e] : 0.0; }
 #else
     (void)rs; (void)rk;
@@ -616,7 +671,7 @@ MPCB_HD const double* stage_record(RecStream& rs, const double* rk, const double
 #if KKT_ON_LANES
     double* R = sm + KktScratch::R;
     W_SYNC();
-#pragma unroll
+MPCB_UNROLL
     for (int q = 0; q < REC_PER_LANE; ++q) { const int e = LANE_ID + N_LANES * q; if (e < R_BWD) R[e] = rs.pre[q]; }
     if (rk_next) rec_prefetch(rs, rk_next);
     W_SYNC();
@@ -627,9 +682,15 @@ MPCB_HD const double* stage_record(RecStream& rs, const double* rk, const double
 #endif
 }
 
+#if KKT_USE_TMA
+typedef RecRing KktIo;
+#else
+struct KktIo { int unused; };
+#endif
+
 // Riccati backward sweep with regularisation dw on every primal variable (and slack).  Returns false when
 // some R_k + B_k' P_{k+1} B_k is not positive definite (wrong inertia).
-MPCB_HD bool ocp_riccati(OcpInst& I, double mu, double dwreg, double* sm) {
+MPCB_HD bool ocp_riccati(OcpInst& I, double mu, double dwreg, double* sm, KktIo& io) {
     const int lane = LANE_ID;
     double* P = sm + KktScratch::P; double* p = sm + KktScratch::p; double* M = sm + KktScratch::M;
     double* q = sm + KktScratch::q; double* T = sm + KktScratch::T; double* f = sm + KktScratch::f;
@@ -659,10 +720,25 @@ MPCB_HD bool ocp_riccati(OcpInst& I, double mu, double dwreg, double* sm) {
     for (int e = lane; e < NXT; e += N_LANES) hT[e] = 0.0;
 #endif
     W_SYNC();
+#if KKT_USE_TMA
+    // the first KKT_NBUF - 1 records are requested up front, record k - (KKT_NBUF - 1) when stage k starts: the copies
+    // stay that many stages ahead of the compute
+    constexpr int AHEAD = KKT_NBUF - 1;
+    if (lane == 0)
+        for (int d = 0; d < AHEAD && NH - 1 - d >= 0; ++d)
+            io.issue((NH - 1 - d) % KKT_NBUF, I.rec + (NH - 1 - d) * REC_SZ, KKT_RBUF, nullptr, 0);
+#else
+    (void)io;
     RecStream rs;
     rec_prefetch(rs, I.rec + (NH - 1) * REC_SZ);
+#endif
     for (int k = NH - 1; k >= 0; --k) {
+#if KKT_USE_TMA
+        if (lane == 0 && k >= AHEAD) io.issue((k - AHEAD) % KKT_NBUF, I.rec + (k - AHEAD) * REC_SZ, KKT_RBUF, nullptr, 0);
+        const double* R = io.wait(k % KKT_NBUF);
+#else
         const double* R = stage_record(rs, I.rec + k * REC_SZ, (k > 0) ? I.rec + (k - 1) * REC_SZ : nullptr, sm);
+#endif
         double* fk = I.frec + k * FREC_SZ;
         // (a) P_{k+1}, p_{k+1} go to the forward record; slack coefficients
         for (int e = lane; e < NXA * NXA; e += N_LANES) fk[FREC_P + e] = P[e];
@@ -732,7 +808,14 @@ MPCB_HD bool ocp_riccati(OcpInst& I, double mu, double dwreg, double* sm) {
                 L[i + NU * j] = a * inv;
             }
         }
-        if (!pd) return false;                                   // uniform across the lanes
+        if (!pd) {                                               // uniform across the lanes
+#if KKT_USE_TMA
+            for (int d = 1; d <= KKT_NBUF - 1; ++d)              // drain the copies in flight before the sweep is repeated
+                if (k >= d) io.wait((k - d) % KKT_NBUF);
+            W_SYNC();
+#endif
+            return false;
+        }
         // (e) K = -Muu^{-1} Mux (NU x NXA), kff = -Muu^{-1} q_u : one column per lane
         for (int c = lane; c <= NXA + NXT; c += N_LANES) {
             double y[NU];
@@ -895,8 +978,13 @@ MPCB_HD void ocp_kkt(OcpInst& I, const OcpShared& S, double* sm) {
     // ---- Newton step by Riccati recursion, inertia-correcting ladder on delta_w
     double dwreg = 0.0;
     bool first = true, ok = false;
+    KktIo io;
+#if KKT_USE_TMA
+    io.init(sm, lane);
+    W_SYNC();
+#endif
     for (int attempt = 0; attempt < 60; ++attempt) {
-        if (ocp_riccati(I, mu, dwreg, sm)) { ok = true; break; }
+        if (ocp_riccati(I, mu, dwreg, sm, io)) { ok = true; break; }
         W_SYNC();
         if (first) { dwreg = (dw_last == 0.0) ? 1e-4 : fmax(1e-20, dw_last / 3.0); first = false; }
         else dwreg *= (dw_last == 0.0) ? 100.0 : 8.0;
@@ -947,12 +1035,23 @@ MPCB_HD void ocp_kkt(OcpInst& I, const OcpShared& S, double* sm) {
     //      one stage ahead, one double per lane)
     double* dxa = sm + KktScratch::dx; double* du = sm + KktScratch::du; double* dxb = sm + KktScratch::dxn;
     for (int i = lane; i < NXA; i += N_LANES) { dxa[i] = 0.0; I.dw[i] = 0.0; }
-#if KKT_ON_LANES
+#if KKT_USE_TMA
+    // [A|B], c head of the record and K, k head of the forward record of stage k: two bulk copies into one ring buffer,
+    // requested two stages ahead.  The forward records were written by this warp's ordinary stores in the backward sweep:
+    // make them visible to the asynchronous proxy first.
+    constexpr int NHEAD = (R_C + NXA + 1) / 2 * 2, NFH = (FREC_P + 1) / 2 * 2;
+    static_assert(NHEAD + NFH <= KKT_RBUF, "forward heads must fit a ring buffer");
+    asm volatile("fence.proxy.async;" ::: "memory");
+    W_SYNC();
+    if (lane == 0)
+        for (int d = 0; d < KKT_NBUF - 1 && d < NH; ++d)
+            io.issue(d % KKT_NBUF, I.rec + d * REC_SZ, NHEAD, I.frec + d * FREC_SZ, NFH);
+#elif KKT_ON_LANES
     constexpr int NHEAD = R_C + NXA, NFH = FREC_P;              // doubles needed per stage: record head, forward-record head
     constexpr int HPL = (NHEAD + NFH + N_LANES - 1) / N_LANES;
     double* Rs = sm + KktScratch::R;                            // staged: [record head | forward-record head]
     double hpre[HPL];
-#pragma unroll
+MPCB_UNROLL
     for (int q = 0; q < HPL; ++q) {
         const int e = lane + N_LANES * q;
         hpre[q] = (e < NHEAD) ? I.rec[e] : ((e < NHEAD + NFH) ? I.frec[e - NHEAD] : 0.0);
@@ -961,12 +1060,16 @@ MPCB_HD void ocp_kkt(OcpInst& I, const OcpShared& S, double* sm) {
     W_SYNC();
     for (int k = 0; k < NH; ++k) {
         double* dx = (k & 1) ? dxb : dxa; double* dxn = (k & 1) ? dxa : dxb;
-#if KKT_ON_LANES
-#pragma unroll
+#if KKT_USE_TMA
+        if (lane == 0 && k + KKT_NBUF - 1 < NH)
+            io.issue((k + KKT_NBUF - 1) % KKT_NBUF, I.rec + (k + KKT_NBUF - 1) * REC_SZ, NHEAD, I.frec + (k + KKT_NBUF - 1) * FREC_SZ, NFH);
+        const double* R = io.wait(k % KKT_NBUF); const double* F = R + NHEAD;
+#elif KKT_ON_LANES
+MPCB_UNROLL
         for (int q = 0; q < HPL; ++q) { const int e = lane + N_LANES * q; if (e < NHEAD + NFH) Rs[e] = hpre[q]; }
         if (k + 1 < NH) {
             const double* rn = I.rec + (k + 1) * REC_SZ; const double* fn = I.frec + (k + 1) * FREC_SZ;
-#pragma unroll
+MPCB_UNROLL
             for (int q = 0; q < HPL; ++q) {
                 const int e = lane + N_LANES * q;
                 hpre[q] = (e < NHEAD) ? rn[e] : ((e < NHEAD + NFH) ? fn[e - NHEAD] : 0.0);
@@ -1070,9 +1173,9 @@ MPCB_HD void ocp_trial_stage(OcpInst& I, const OcpShared& S, int k) {
     const double al = I.st->alpha, rf = S.o.bound_relax;
     const double* w = I.w; const double* dw = I.dw;
     double z[NXA], u[NU], d[ND + 1], px[NPX + 1], py[NPY + 1], t0, xn[NXA];
-#pragma unroll
+MPCB_UNROLL
     for (int i = 0; i < NXA; ++i) z[i] = w[k * NZA + i] + al * dw[k * NZA + i];
-#pragma unroll
+MPCB_UNROLL
     for (int i = 0; i < NU; ++i) u[i] = w[k * NZA + NXA + i] + al * dw[k * NZA + NXA + i];
     stage_params(I.par, k, d, px, py, &t0);
     double th = 0.0, prod = 1.0, l;     // prod: product of slacks-to-bounds (one log per stage)
@@ -1080,21 +1183,21 @@ MPCB_HD void ocp_trial_stage(OcpInst& I, const OcpShared& S, int k) {
     {
         ContCtx cc; cc.u = u; cc.par = I.par; cc.pxk = px; cc.pyk = py;
         double xt[NX + 1], xe[NX + 1];
-#pragma unroll
+MPCB_UNROLL
         for (int i = 0; i < NX; ++i) xt[i] = z[i];
         xt[NX] = 0.0;
         rk4_value_t<SysCont>(xt, cc, t0, xe);
-#pragma unroll
+MPCB_UNROLL
         for (int i = 0; i < NX; ++i) xn[i] = xe[i];
         l = xe[NX];
     }
 #else
     dyn_value(z, u, d, px, t0, xn);
-#pragma unroll
+MPCB_UNROLL
     for (int i = NX; i < NXA; ++i) xn[i] = u[i - NX];
     ocp_cost(z, u, I.par, px, py, &l);
 #endif
-#pragma unroll
+MPCB_UNROLL
     for (int i = 0; i < NXA; ++i) th += fabs(xn[i] - (w[(k + 1) * NZA + i] + al * dw[(k + 1) * NZA + i]));
 #if NG > 0
     {

@@ -382,6 +382,10 @@ static void tgt_solve_resto(const double* par, double* w, double* fout, int* sta
 }
 
 MPCB_HD void tgt_solve(const double* par, double* w, double* fout, int* status_out, int* iters_out, const TgtShared& S) {
+#if MPCB_DENSE_SH
+    tgt_solve_t<true>(par, w, fout, status_out, iters_out, S);        // large models: one variant (compile time, stack)
+    return;
+#endif
     double w0[NWS];
     for (int i = 0; i < NWS; ++i) w0[i] = w[i];
     tgt_solve_t<false>(par, w, fout, status_out, iters_out, S);

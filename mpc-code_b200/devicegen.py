@@ -57,6 +57,36 @@ def _cached_variants(prefix: str, base, f, vjp_in, vjp_out, sh_in, sh_out, taint
     return fns, len(nodes), len(recips)
 
 
+# Above this many entries of the sensitivity block S (nx x (nx + nu)) the products of the model's derivatives with S are no
+# longer generated symbolically: their size grows like nx^2 (nx + nu)^2 (26 minutes of nvcc and 266 kB of stack per thread
+# for 20 states in round 1).  The generator then emits only the DENSE Jacobian and the nu-weighted Hessian of the
+# right-hand side, and the device code forms K = f_x S + [0|f_u], f_x' nu and [S;E]'(nu' d2f)[S;E] with loops
+# (MPCB_DENSE_SH, csrc/mpcb_device.cuh).  Override with the environment variable MPCB_DENSE_SH=0/1.
+DENSE_SH_ENTRIES = 200
+
+
+def _use_dense(nx: int, nu: int) -> bool:
+    import os
+    env = os.environ.get("MPCB_DENSE_SH")
+    if env in ("0", "1"):
+        return env == "1"
+    return nx * (nx + nu) > DENSE_SH_ENTRIES
+
+
+def _rhs_functions_dense(prefix: str, rhs: Function, nx: int, nu: int, nd: int, npx: int, nxi: int) -> List[CFunction]:
+    """Right-hand side with its dense first derivatives and the adjoint-weighted Hessian (large models)."""
+    x, u, d, t, px = [SX.sym(n, k) for n, k in (("x", nx), ("u", nu), ("d", nd), ("t", 1), ("px", npx))]
+    f = rhs(x, u, d, t, px)
+    base = [("x", x), ("u", u), ("d", d), ("t", t), ("px", px)]
+    nu_adj = SX.sym("nu", nx)
+    Hf, _ = hessian(mtimes(nu_adj.T, f), vertcat(x, u))
+    jd = jacobian(f, d) if (nxi > nx and nd) else SX.zeros(nx, 0)
+    _rhs_functions.last_cache = (0, 0)
+    return [CFunction(prefix + "f", base, [("xdot", f)]),
+            CFunction(prefix + "f_jac", base, [("xdot", f), ("Jx", jacobian(f, x)), ("Ju", jacobian(f, u)), ("Jd", jd)]),
+            CFunction(prefix + "f_hess", base + [("nu", nu_adj)], [("M", tril_pack(Hf))])]
+
+
 def _rhs_functions(prefix: str, rhs: Function, nx: int, nu: int, nd: int, npx: int, nxi: int) -> List[CFunction]:
     """Right-hand side ``f(x,u,d,t,px)`` with the products the RK4 sweeps need."""
     x, u, d, t, px = [SX.sym(n, k) for n, k in (("x", nx), ("u", nu), ("d", nd), ("t", 1), ("px", npx))]
@@ -125,7 +155,9 @@ def generate_header(prob, ss_spec, ocp_spec, opts: Optional[Dict] = None) -> Dic
     if kind == "rk4":
         D["MPCB_DYN_RK4"] = 1
         D["MPCB_MX"] = int(prob.Fx_model.meta["substeps"])
-        fns += _rhs_functions("mdl_", prob.Fx_model.meta["rhs"], nx, nu, nd, npx, prob.nxi)
+        dense = _use_dense(nx, nu)
+        D["MPCB_DENSE_SH"] = int(dense)
+        fns += (_rhs_functions_dense if dense else _rhs_functions)("mdl_", prob.Fx_model.meta["rhs"], nx, nu, nd, npx, prob.nxi)
         D["MPCB_MDL_NC"], D["MPCB_MDL_NR"] = _rhs_functions.last_cache
         d_, px_ = SX.sym("d", nd), SX.sym("px", npx)
         post = prob.Fx_model.meta["post"](d_, px_)
@@ -133,6 +165,7 @@ def generate_header(prob, ss_spec, ocp_spec, opts: Optional[Dict] = None) -> Dic
     else:
         D["MPCB_DYN_RK4"] = 0
         D["MPCB_MX"] = 1
+        D["MPCB_DENSE_SH"] = 0
         fns += _discrete_functions("mdl_", prob.Fx_model, nx, nu, nd, npx, prob.nxi)
     x, u, d, t, py = s["x"], s["u"], s["d"], s["t"], s["py"]
     Fy = prob.Fy_model(x, u, d, t, py)
@@ -171,6 +204,8 @@ def generate_header(prob, ss_spec, ocp_spec, opts: Optional[Dict] = None) -> Dic
         o = ocp_spec
         if o.flags["ContForm"] is True and o.uses_uprev:
             raise NotImplementedError("ContForm together with Delta-u terms is not on the device path")
+        if o.flags["ContForm"] is True and D.get("MPCB_DENSE_SH"):
+            raise NotImplementedError("ContForm is not available for large models (dense derivative products)")
         if o.term_eq is not None:                       # TermCons: X_N - x_s = 0 (X_N = 0 without QForm), Control_Calc.py:194-198
             Jt = jacobian(o.term_eq, o.XN)
             ident = all((e.op == "const" and float(e.val) == (1.0 if i % (o.n + 1) == 0 else 0.0)) for i, e in enumerate(Jt.elements()))

@@ -169,3 +169,94 @@ def test_closed_loop_large_batch_of_synthetic_plants():
     assert int((rec["STATUS_DYN"] != 0).sum()) == 0
     assert float(rec["Xp"][-1].abs().max()) < float(rec["Xp"][0].abs().max())
     assert float(rec["U"].abs().max()) <= 1.0 + 1e-7
+
+
+# ---- large-state members: dense derivative products (devicegen.DENSE_SH_ENTRIES, MPCB_DENSE_SH) ---------------------
+def _single_shooting_reference_batched(ns, xhat):
+    """As `_single_shooting_reference`, with the complex-step gradient evaluated for all inputs at once."""
+    import scipy.optimize as sopt
+    m_ = ns["_synthetic"]
+    Ac, Bc, W, nx, nu, N = m_["Ac"], m_["Bc"], m_["W"], m_["nx"], m_["nu"], m_["N"]
+    h, Mx = 0.1, 4
+
+    def f(x, u):                                   # x [..., nx], u [..., nu]
+        return x @ Ac.T + u @ Bc.T + 0.1 * np.tanh(x @ W.T)
+
+    def rollout(U):                                # U [..., N*nu] -> cost [...], states
+        x = np.broadcast_to(xhat.astype(U.dtype), U.shape[:-1] + (nx,)); J = 0.0; X = [x]
+        hs = h / Mx
+        for k in range(N):
+            u = U[..., k * nu:(k + 1) * nu]
+            J = J + 0.5 * ((x * x).sum(-1) + 0.1 * (u * u).sum(-1))
+            for _ in range(Mx):
+                k1 = f(x, u); k2 = f(x + 0.5 * hs * k1, u); k3 = f(x + 0.5 * hs * k2, u); k4 = f(x + hs * k3, u)
+                x = x + hs / 6.0 * (k1 + 2 * k2 + 2 * k3 + k4)
+            X.append(x)
+        return J, X
+
+    def fun(U):
+        Uc = np.tile(U.astype(complex), (U.size, 1)) + 1e-30j * np.eye(U.size)
+        g = rollout(Uc)[0].imag / 1e-30
+        return float(rollout(U)[0]), g
+    res = sopt.minimize(fun, np.zeros(N * nu), jac=True, method="L-BFGS-B", bounds=[(-1.0, 1.0)] * (N * nu),
+                        options=dict(maxiter=5000, ftol=1e-16, gtol=1e-11, maxcor=60))
+    J, X = rollout(res.x)
+    return res.x.reshape(N, nu), np.array(X), float(J)
+
+
+def test_dense_derivative_products_equal_the_generated_ones(monkeypatch):
+    """The looped dense products used for large models against the symbolically generated ones (which the oracle pins)."""
+    from conftest import Bundle
+    b = _bundle("syn_4_2_70")
+    par, w0 = _cases(b, 3)
+    w, f, st, it, _ = b.harness_ocp(par, w0)
+    monkeypatch.setenv("MPCB_DENSE_SH", "1")
+    bd = Bundle("syn_4_2_70")
+    assert bd.lib["gen"]["defines"]["MPCB_DENSE_SH"] == 1 and b.lib["gen"]["defines"]["MPCB_DENSE_SH"] == 0
+    wd, fd, std, itd, _ = bd.harness_ocp(par, w0)
+    assert np.array_equal(st, std) and np.array_equal(it, itd)
+    assert np.abs(w - wd).max() < 1e-10 and np.all(np.abs(f - fd) <= 1e-11 * np.maximum(1.0, np.abs(f)))
+
+
+def _twenty_state_case():
+    b = _bundle("syn_20_6_20")
+    p = b.prob
+    xhat = np.random.default_rng(20).uniform(-1, 1, p.nx)
+    return b, p, xhat, b.ocp_par(xhat, np.zeros(p.nx), np.zeros(p.nu), np.zeros(0))
+
+
+def test_twenty_state_member_matches_an_independent_single_shooting_solution():
+    """BASELINE configs[4] at its largest model size (20 states, 6 inputs): device code on the CPU."""
+    b, p, xhat, par = _twenty_state_case()
+    assert b.lib["gen"]["defines"]["MPCB_DENSE_SH"] == 1
+    w, f, st, it, _ = b.harness_ocp(par, np.zeros(p.nw))
+    U, X, J = _single_shooting_reference_batched(p.ns, xhat)
+    nz = p.nx + p.nu
+    Ud = w[0, :nz * p.N].reshape(p.N, nz)[:, p.nx:]
+    assert st[0] == 0
+    assert np.abs(Ud - U).max() < 1e-5 and abs(f[0] - J) <= 1e-8 * max(1.0, abs(J))
+    assert np.abs(Ud).max() <= 1.0 + 1e-7
+
+
+@pytest.mark.gpu
+def test_gpu_twenty_state_member():
+    from mpc_code_b200.mpc_loop import CompiledProblem
+    from mpc_code_b200.solvers import BatchedNlpSolver, MpcbHandle
+    b, p, xhat, par = _twenty_state_case()
+    wc, fc, stc, itc, _ = b.harness_ocp(par, np.zeros(p.nw))
+    cp = CompiledProblem(p, "syn_20_6_20")
+    h = MpcbHandle(cp.library, 3, dict(max_iter=100), dict(max_iter=100))
+    solver = BatchedNlpSolver("ocp", cp.ocp_spec).attach(h)
+    sol = solver(x0=np.zeros((3, p.nw)), p=np.tile(par, (3, 1)))
+    w = sol["x"].cpu().numpy()
+    assert np.all(solver.stats()["status"].cpu().numpy() == 0) and np.array_equal(w[0], w[2])
+    assert np.array_equal(solver.stats()["iter_count"].cpu().numpy(), np.repeat(itc, 3))
+    assert np.abs(w[0] - wc[0]).max() < 1e-8 and abs(float(sol["f"][0]) - fc[0]) <= 1e-9 * max(1.0, abs(fc[0]))
+    # closed loop through the fused step: estimator (20 x 20 covariance), target (50 x 50 KKT), OCP
+    B = 64
+    x0 = np.random.default_rng(21).uniform(-1, 1, (B, p.nx))
+    ctl = cp.controller(B)
+    ctl.reset(x0_p=x0, x0_m=x0)
+    rec = ctl.run(4, fused=True)
+    assert int((rec["STATUS_DYN"] != 0).sum()) == 0 and float(rec["U"].abs().max()) <= 1.0 + 1e-7
+    assert float(rec["Xp"][-1].abs().max()) < float(rec["Xp"][0].abs().max())
