@@ -131,3 +131,69 @@ def test_gpu_restoration_and_failure_policy(enmpc, nmpc):
         assert (r["STATUS_DYN"] == -1).all()
         moved = (r["U"] - torch.as_tensor(pn.u0, device=r["U"].device)).abs().max().item() > 1e-9
         assert moved != hold
+
+
+def _lp_case(b):
+    xh = np.array([3.0, 2.5, 2.0]); xs = np.array([0.2, 0.1, 0.0]); us = np.array([0.5, -0.3])
+    par = b.ocp_par(xh, xs, us, np.zeros(3))
+    lb, ub = b.ocp.w_lb.copy(), b.ocp.w_ub.copy(); lb[:3] = ub[:3] = xh
+    return par, lb, ub
+
+
+def test_lp_form_costs_device_code_follows_the_oracle():
+    """Stage cost r_x |x - xs| + r_u |u - us| (`r_x` / `r_u`, Utilities.py:341-352): `fabs` / `sign` through the code
+    generator.  The problem is nonsmooth at its solution, so interior-point iterates are compared, not a converged point:
+    the same unfinished iterate at iteration limits 3 and 6, and the same verdict (line search and restoration fail, status
+    2 after 6 iterations) without a limit."""
+    from conftest import _bundle
+    b = _bundle("lmpc_cstr_lp")
+    par, lb, ub = _lp_case(b)
+    on = OcpNlp(b.ocp, b.oracle)
+    for max_iter, status in ((3, -1), (6, -1), (100, 2)):
+        w, f, st, it, _ = b.harness_ocp(par, b.cold_guess(), max_iter=max_iter)
+        r = on.solve(b.cold_guess(), par, lb, ub, opts=IpmOptions(max_iter=max_iter))
+        assert st[0] == r.status == status and it[0] == r.iters
+        assert np.abs(w[0] - r.x).max() < 1e-9 and abs(f[0] - r.f) <= 1e-10 * max(1.0, abs(r.f))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kw,okw", [
+    (dict(honor_original_bounds=1), dict(honor_original_bounds=True)),
+    (dict(mu_init=1e-2), dict(mu_init=1e-2)),
+    (dict(tol=1e-6), dict(tol=1e-6)),
+    (dict(bound_relax_factor=0.0), dict(bound_relax_factor=0.0)),
+])
+def test_gpu_option_variants_follow_the_oracle(nmpc, kw, okw):
+    """The option variants of `test_option_variants_follow_the_oracle` on the device (IPOPT 3.12 / 3.14 bound handling,
+    barrier start, tolerance, no bound relaxation)."""
+    from mpc_code_b200.mpc_loop import CompiledProblem
+    from mpc_code_b200.solvers import MpcbHandle, BatchedNlpSolver
+    cp = CompiledProblem(nmpc.prob, "nmpc_cstr")
+    par, lb, ub = _case(nmpc, seed=3)
+    h = MpcbHandle(cp.library, 2, dict(max_iter=100), dict(max_iter=100, **kw))
+    solver = BatchedNlpSolver("ocp", cp.ocp_spec).attach(h)
+    sol = solver(x0=np.tile(nmpc.cold_guess(), (2, 1)), p=np.tile(par, (2, 1)))
+    r = OcpNlp(nmpc.ocp, nmpc.oracle).solve(nmpc.cold_guess(), par, lb, ub, opts=IpmOptions(max_iter=100, **okw))
+    w = sol["x"].cpu().numpy()
+    assert int(solver.stats()["status"][0]) == r.status == 0 and int(solver.stats()["iter_count"][0]) == r.iters
+    assert np.abs(w[0] - r.x).max() < 1e-6 and abs(float(sol["f"][0]) - r.f) <= 1e-8 * max(1.0, abs(r.f))
+    if "honor_original_bounds" in kw:
+        assert np.all(w[0] >= lb - 1e-15) and np.all(w[0] <= ub + 1e-15)
+
+
+@pytest.mark.gpu
+def test_gpu_lp_form_costs():
+    from conftest import _bundle
+    from mpc_code_b200.mpc_loop import CompiledProblem
+    from mpc_code_b200.solvers import MpcbHandle, BatchedNlpSolver
+    b = _bundle("lmpc_cstr_lp")
+    par, lb, ub = _lp_case(b)
+    cp = CompiledProblem(b.prob, "lmpc_cstr_lp")
+    on = OcpNlp(b.ocp, b.oracle)
+    for max_iter, status in ((6, -1), (100, 2)):
+        h = MpcbHandle(cp.library, 2, dict(max_iter=100), dict(max_iter=max_iter))
+        solver = BatchedNlpSolver("ocp", cp.ocp_spec).attach(h)
+        sol = solver(x0=np.tile(b.cold_guess(), (2, 1)), p=np.tile(par, (2, 1)))
+        r = on.solve(b.cold_guess(), par, lb, ub, opts=IpmOptions(max_iter=max_iter))
+        assert int(solver.stats()["status"][0]) == r.status == status and int(solver.stats()["iter_count"][0]) == r.iters
+        assert np.abs(sol["x"].cpu().numpy()[0] - r.x).max() < 1e-8
