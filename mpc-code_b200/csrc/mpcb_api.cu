@@ -178,7 +178,14 @@ __global__ void __launch_bounds__(64) k_target(int B, const double* par, double*
                                                TgtShared S) {
     const int inst = blockIdx.x * blockDim.x + threadIdx.x;
     if (inst >= B) return;
-    tgt_solve(par + (size_t)inst * MPCB_NPARSS, w + (size_t)inst * NWS, f + inst, status + inst, iters + inst, S);
+    tgt_solve_regular(par + (size_t)inst * MPCB_NPARSS, w + (size_t)inst * NWS, f + inst, status + inst, iters + inst, S);
+}
+// the rare instances whose line search failed: restoration variant (see tgt_solve_regular)
+__global__ void __launch_bounds__(64) k_target_resto(int B, const double* par, double* w, double* f, int* status, int* iters,
+                                                     TgtShared S) {
+    const int inst = blockIdx.x * blockDim.x + threadIdx.x;
+    if (inst >= B) return;
+    tgt_solve_resto(par + (size_t)inst * MPCB_NPARSS, w + (size_t)inst * NWS, f + inst, status + inst, iters + inst, S);
 }
 #endif
 
@@ -795,6 +802,10 @@ int mpcb_target(mpcb_handle_t h, const double* par_ss, double* wss, double* fss,
 #if MPCB_HAS_TARGET
     TgtShared S; S.lbx = h->ss_lbx; S.ubx = h->ss_ubx; S.o = to_ipm(h->opts_ss);
     { Prof p(h, (cudaStream_t)stream, KC_TARGET); k_target<<<nblk(h->B, MPCB_TGT_BLOCK), MPCB_TGT_BLOCK, 0, (cudaStream_t)stream>>>(h->B, par_ss, wss, fss, status, iters, S); }
+#if !MPCB_DENSE_SH
+    { Prof p(h, (cudaStream_t)stream, KC_TARGET); k_target_resto<<<nblk(h->B, MPCB_TGT_BLOCK), MPCB_TGT_BLOCK, 0, (cudaStream_t)stream>>>(h->B, par_ss, wss, fss, status, iters, S); }
+    h->host_launches += 1;
+#endif
     CK(cudaGetLastError());
     if (h->profile) { CK(cudaStreamSynchronize((cudaStream_t)stream)); prof_collect(h); }
     h->host_launches += 1; h->last_stream = (cudaStream_t)stream;

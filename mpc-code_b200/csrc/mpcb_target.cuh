@@ -186,15 +186,17 @@ MPCB_HD void tgt_solve_t(const double* par, double* w, double* fout, int* status
     double mu = o.mu_init, tau = fmax(0.99, 1.0 - mu), dw_last = 0.0, theta0 = -1.0;
     double filt[2 * MPCB_MAXFILT]; int nfilt = 0, acc = 0, it = 0, status = -1;
     bool resto = false; int resto_calls = 0; double theta_entry = 0.0;      // feasibility restoration, as in ocp_accept
-    double f, c[MCS], grad[NWS], J[MCS * NWS], Hp[NWSP];
-    tgt_eval(w, par, y, true, &f, c, grad, J, Hp);
-    {   // IPOPT: a starting point whose functions do not evaluate ends the solve with Invalid_Number_Detected (-13)
-        double chk = f;
-        for (int i = 0; i < MCS; ++i) chk += c[i];
-        for (int i = 0; i < NWS; ++i) chk += grad[i];
-        if (!(chk == chk) || !fin(chk)) { *fout = f; *status_out = -13; *iters_out = 0; return; }
-    }
-    while (true) {
+    double f = 0.0, c[MCS], grad[NWS], J[MCS * NWS], Hp[NWSP];
+    bool evaluate = true;               // ONE call site of the derivative evaluation (three inlined RK4 sweeps): the solver's
+    while (true) {                      // code is 240 kB otherwise and a sixth of its stalls are instruction fetches
+        if (evaluate) tgt_eval(w, par, y, true, &f, c, grad, J, Hp);
+        evaluate = false;
+        if (it == 0 && !resto) {        // IPOPT: a starting point whose functions do not evaluate ends the solve with -13
+            double chk = f;
+            for (int i = 0; i < MCS; ++i) chk += c[i];
+            for (int i = 0; i < NWS; ++i) chk += grad[i];
+            if (!(chk == chk) || !fin(chk)) { status = -13; break; }
+        }
         // optimality error
         double dual = 0.0, prim = 0.0, ysum = 0.0, zsum = 0.0, c0 = 0.0;
         for (int j = 0; j < NWS; ++j) {
@@ -328,7 +330,7 @@ MPCB_HD void tgt_solve_t(const double* par, double* w, double* fout, int* status
             if (leave) for (int i = 0; i < nfilt; ++i) if (th_t >= filt[2 * i] && ph_t >= filt[2 * i + 1]) { leave = false; break; }
             if (leave) resto = false;
             it += 1;
-            tgt_eval(w, par, y, true, &f, c, grad, J, Hp);
+            evaluate = true;
             continue;
         }
         while (alpha >= amin * (1.0 - 1e-12) && alpha > 1e-16) {
@@ -364,7 +366,7 @@ MPCB_HD void tgt_solve_t(const double* par, double* w, double* fout, int* status
         }
         for (int i = 0; i < MCS; ++i) y[i] += alpha * rhs[NWS + i];
         it += 1;
-        tgt_eval(w, par, y, true, &f, c, grad, J, Hp);
+        evaluate = true;
     }
     if (o.honor_original_bounds) {
         for (int j = 0; j < NWS; ++j) w[j] = fmin(fmax(w[j], S.lbx[j]), S.ubx[j]);
@@ -374,29 +376,28 @@ MPCB_HD void tgt_solve_t(const double* par, double* w, double* fout, int* status
     *fout = f; *status_out = status; *iters_out = it;
 }
 
-#ifdef __CUDACC__
-__device__ __noinline__
-#endif
-static void tgt_solve_resto(const double* par, double* w, double* fout, int* status_out, int* iters_out, const TgtShared& S) {
-    tgt_solve_t<true>(par, w, fout, status_out, iters_out, S);
-}
-
-MPCB_HD void tgt_solve(const double* par, double* w, double* fout, int* status_out, int* iters_out, const TgtShared& S) {
+// Regular variant first; an instance whose line search fails is handed back with status TGT_NEEDS_RESTO and its
+// initial guess restored, and solved again (cold start: the same iterates up to that point) by the restoration variant -
+// on the device by a second kernel (k_target_resto) that exits at once for every other instance, so that the common
+// kernel does not carry the restoration code (it doubles the solver's instruction footprint).
+MPCB_HD void tgt_solve_regular(const double* par, double* w, double* fout, int* status_out, int* iters_out, const TgtShared& S) {
 #if MPCB_DENSE_SH
     tgt_solve_t<true>(par, w, fout, status_out, iters_out, S);        // large models: one variant (compile time, stack)
-    return;
-#endif
+#else
     double w0[NWS];
     for (int i = 0; i < NWS; ++i) w0[i] = w[i];
     tgt_solve_t<false>(par, w, fout, status_out, iters_out, S);
-    if (*status_out == TGT_NEEDS_RESTO) {
+    if (*status_out == TGT_NEEDS_RESTO)
         for (int i = 0; i < NWS; ++i) w[i] = w0[i];
-#ifdef __CUDA_ARCH__
-        tgt_solve_resto(par, w, fout, status_out, iters_out, S);
-#else
-        tgt_solve_t<true>(par, w, fout, status_out, iters_out, S);
 #endif
-    }
+}
+MPCB_HD void tgt_solve_resto(const double* par, double* w, double* fout, int* status_out, int* iters_out, const TgtShared& S) {
+    if (*status_out == TGT_NEEDS_RESTO) tgt_solve_t<true>(par, w, fout, status_out, iters_out, S);
+}
+// host callers (tests, CPU baseline): both in sequence
+MPCB_HD void tgt_solve(const double* par, double* w, double* fout, int* status_out, int* iters_out, const TgtShared& S) {
+    tgt_solve_regular(par, w, fout, status_out, iters_out, S);
+    tgt_solve_resto(par, w, fout, status_out, iters_out, S);
 }
 #endif  // MPCB_HAS_TARGET
 
