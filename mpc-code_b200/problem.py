@@ -71,8 +71,8 @@ def build_problem(ns: Dict[str, Any]) -> MpcProblem:
     else:  # :45-48
         npx, npxp, npy, npyp = nx, nxp, ny, ny
     N, h = int(ns["N"]), float(ns["h"])
-    if ns.get("ssjacid") is True or ns.get("Adaptation") is True or ns.get("Collocation") is True:
-        raise NotImplementedError("ssjacid / Adaptation / Collocation are outside the accelerated path")
+    if ns.get("Adaptation") is True or ns.get("Collocation") is True:
+        raise NotImplementedError("Adaptation / Collocation are outside the accelerated path")
     if ns.get("slacks") is True:
         raise NotImplementedError("soft-constraint slacks are outside the accelerated path (no shipped example enables them)")
 
@@ -92,7 +92,10 @@ def build_problem(ns: Dict[str, Any]) -> MpcProblem:
 
     # model ladder (:93-167) - the branches differ only in which keywords are forwarded
     kw: Dict[str, Any] = dict(dist)
-    if "User_fxm_Cont" in ns:
+    if ns.get("ssjacid") is True:                                   # (:84-91) linearise the nonlinear model at a steady state
+        from .ss_jac_id import linear_model_from_ssjacid
+        Fx_model, Fy_model = linear_model_from_ssjacid(ns, x, u, y, d, k, t, px, py)
+    elif "User_fxm_Cont" in ns:
         kw.update(fx=ns["User_fxm_Cont"], Mx=ns["Mx"])
         if SF is True: kw.update(SF=SF)
         elif "User_fym" in ns: kw.update(fy=ns["User_fym"])
@@ -115,7 +118,8 @@ def build_problem(ns: Dict[str, Any]) -> MpcProblem:
             if "xlin" in ns: kw.update(xlin=ns["xlin"], ulin=ns["ulin"])
     else:
         raise ValueError("no model: define User_fxm_Cont, User_fxm_Dis or A/B")
-    Fx_model, Fy_model = defF_model(x, u, y, d, k, t, px, py, offree, LinPar, **kw)
+    if ns.get("ssjacid") is not True:
+        Fx_model, Fy_model = defF_model(x, u, y, d, k, t, px, py, offree, LinPar, **kw)
 
     # plant (:171-196)
     if ns["Fp_nominal"] is True:
