@@ -161,7 +161,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": 0, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": _config(1, n_inst, None),
+        "config": _config(max(1, args.gpus)),
         "cpu_baseline": {"value": value, "unit": "steps/s", "cores": threads, "kind": "port", "sample": sample},
         "cpu_baseline_numpy": {"value": v2, "unit": "steps/s", "cores": cores, "kind": "port",
                                "sample": "%d instances x 20 consecutive steps after %d cold-start steps, one process per core "
@@ -170,18 +170,13 @@ def run_reference(args):
         "gpu_launches": 0})
 
 
-def _config(world, batch_per_rank, groups, extra=None):
-    """`config` of both arms: the same workload description (the arms differ in the sample size they time)."""
-    c = {"workload": "Ex_NMPC (configs[1]): CSTR NMPC + EKF + target, N=50, Mx=10, closed loop with plant and measurement "
-                     "noise; x0 perturbed 2%%/0.2%%/2%% (seed %d)" % SEED_X0,
-         "batch_per_gpu": BATCH_PER_GPU, "global_batch": world * BATCH_PER_GPU,
-         "parallelism": "instances sharded, %d rank(s)" % world}
-    if batch_per_rank != BATCH_PER_GPU:
-        c["sample_instances"] = batch_per_rank
-    if groups is not None:
-        c["instance_groups_per_gpu"] = groups
-    c.update(extra or {})
-    return c
+def _config(world):
+    """`config` of BOTH arms, key for key: the workload (the CPU arm times a bounded sample of it, described in its
+    `cpu_baseline.sample`; GPU-arm specifics - instance groups, cache note - are top-level keys of its line)."""
+    return {"workload": "Ex_NMPC (configs[1]): CSTR NMPC + EKF + target, N=50, Mx=10, closed loop with plant and measurement "
+                        "noise; x0 perturbed 2%%/0.2%%/2%% (seed %d)" % SEED_X0,
+            "batch_per_gpu": BATCH_PER_GPU, "global_batch": world * BATCH_PER_GPU,
+            "parallelism": "instances sharded, %d rank(s)" % world}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -450,8 +445,8 @@ def run_gpu(args):
         "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": elapsed_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": _config(world, B, groups, {"cache": "per-step working set %.0f MB per GPU > 126 MB L2 (no flush needed)"
-                                                      % (B * cp_ws_bytes(cp) / 1e6)}),
+        "config": _config(world), "instance_groups_per_gpu": groups,
+        "cache": "per-step working set %.0f MB per GPU > 126 MB L2 (no flush needed)" % (B * cp_ws_bytes(cp) / 1e6),
         "p50_step_latency_ms": float(np.median(step_ms)), "p99_step_latency_ms": float(np.percentile(step_ms, 99)),
         "slowest_steps": [[int(i), float(step_ms[i])] for i in np.argsort(-step_ms)[:3]],
         "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": B * prob.ny * 8, "d2h_bytes_per_step": B * prob.nu * 8,
