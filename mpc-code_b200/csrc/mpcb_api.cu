@@ -87,7 +87,15 @@ __global__ void EVAL_BOUNDS k_ocp_eval(OcpArgs a) {
 #define KKT_WARPS (4 * KKT_SCRATCH_BYTES <= 48 * 1024 ? 4 : (2 * KKT_SCRATCH_BYTES <= 48 * 1024 ? 2 : 1))
 #endif
 #if MPCB_KKT_LANES > 1
-__global__ void __launch_bounds__(32 * KKT_WARPS) k_ocp_kkt(OcpArgs a) {
+// -DMPCB_FUSE_LS=1 (opt-in, one warp per instance only): the warp that computed the step also runs the instance's filter
+// line search - trial points over its lanes (stage k on lane k mod 32), decision, backtracking - so a tick is two
+// kernels (k_ocp_eval, k_ocp_kkt).  Same device functions and arithmetic as the four-kernel tick, GPU suite green, but
+// SLOWER on Ex_NMPC (612 k vs 687 k steps/s, profiles/r02_variants_fuse.txt): the RK4 roll-outs of the trial run at the
+// KKT kernel's 7 warps per scheduler and pay their full latency, the separate k_ocp_trial hides it with 4x the warps.
+#ifndef MPCB_FUSE_LS
+#define MPCB_FUSE_LS 0
+#endif
+__global__ void __launch_bounds__(32 * KKT_WARPS) k_ocp_kkt(OcpArgs a, int* n_active) {
     constexpr int GROUPS = 32 * KKT_WARPS / MPCB_KKT_LANES;        // instances per block
     __shared__ __align__(16) double scratch[GROUPS][KktScratch::total];
     const int inst = (blockIdx.x * blockDim.x + threadIdx.x) / MPCB_KKT_LANES;
@@ -95,10 +103,25 @@ __global__ void __launch_bounds__(32 * KKT_WARPS) k_ocp_kkt(OcpArgs a) {
     if (a.st[inst].state != ST_EVAL) return;
     OcpInst I = ocp_view(a, inst);
     ocp_kkt(I, a.S, scratch[threadIdx.x / MPCB_KKT_LANES]);
+#if MPCB_FUSE_LS
+    const int lane = threadIdx.x & 31;
+    volatile int* state = &a.st[inst].state;
+    while (*state == ST_LS) {
+        if (lane == 0) atomicAdd(a.counters + 1, 1ULL);
+        for (int k = lane; k < NH; k += 32) ocp_trial_stage(I, a.S, k);
+        __syncwarp();
+        ocp_accept(I, a.S);
+    }
+    if (n_active && lane == 0 && *state != ST_DONE) atomicAdd(n_active, 1);
+#else
+    (void)n_active;
+#endif
 }
 #define KKT_GRID(B) nblk((long)(B) * MPCB_KKT_LANES, 32 * KKT_WARPS), 32 * KKT_WARPS
 #else
-__global__ void __launch_bounds__(32) k_ocp_kkt(OcpArgs a) {
+#define MPCB_FUSE_LS 0
+__global__ void __launch_bounds__(32) k_ocp_kkt(OcpArgs a, int* n_active) {
+    (void)n_active;
     const int inst = blockIdx.x * blockDim.x + threadIdx.x;
     if (inst >= a.B) return;
     if (a.st[inst].state != ST_EVAL) return;
@@ -605,19 +628,20 @@ static bool same_opts(const mpcb_opts_t& a, const mpcb_opts_t& b) {
 #if MPCB_HAS_OCP
 // Build the device-driven solve as a CUDA graph:
 //   memset counters -> k_ocp_init -> U unrolled ticks -> k_ocp_cond -> WHILE { tick -> k_ocp_cond } -> k_ocp_output
-// with tick = k_ocp_eval -> k_ocp_kkt -> k_ocp_trial -> k_ocp_accept.  The loop condition is set on the device by k_ocp_cond
+// with tick = k_ocp_eval -> k_ocp_kkt (line search inside; four kernels with -DMPCB_FUSE_LS=0).  The loop condition is set on the device by k_ocp_cond
 // (cudaGraphSetConditional), so a whole solve - however many ticks its slowest instance needs - is ONE graph launch and the
 // host never waits on it (round 1 polled a device counter every two ticks, with one spinning host thread per group).
 // The first U ticks are plain kernel nodes: a node inside a WHILE body costs ~5 us of device-side scheduling that
 // serialises across streams (measured: profiles/r02_groups_sweep_graph.txt), a plain node ~1.5 us, and a tick whose
 // instances are all done is four kernels that exit at once.  U = MPCB_GRAPH_UNROLL (environment), default 10: a warm
 // closed-loop step of Ex_NMPC needs 11-13 ticks.
+#define TICK_KERNELS (MPCB_FUSE_LS ? 2 : 4)
 static int add_tick(mpcb_ctx* h, cudaGraph_t g, cudaGraphNode_t* dep, int ndep, OcpArgs& a, int* n_active, cudaGraphNode_t* last) {
     const int bs = 128;
     const long nst = (long)h->B * NH;
     cudaKernelNodeParams kp; memset(&kp, 0, sizeof(kp));
     void* args1[] = {&a};
-    cudaGraphNode_t n_eval, n_kkt, n_trial;
+    cudaGraphNode_t n_eval;
     kp.kernelParams = args1;
     kp.func = (void*)k_ocp_eval; kp.gridDim = dim3(nblk(nst, MPCB_EVAL_BLOCK)); kp.blockDim = dim3(MPCB_EVAL_BLOCK);
     kp.sharedMemBytes = (unsigned)EVAL_SMEM_BYTES;
@@ -625,13 +649,21 @@ static int add_tick(mpcb_ctx* h, cudaGraph_t g, cudaGraphNode_t* dep, int ndep, 
     kp.sharedMemBytes = 0;
     { dim3 gk(1), bk(1); auto set = [&](int gx, int bx) { gk = dim3(gx); bk = dim3(bx); }; set(KKT_GRID(h->B));
       kp.func = (void*)k_ocp_kkt; kp.gridDim = gk; kp.blockDim = bk; }
+    void* args2[] = {&a, &n_active};
+    kp.kernelParams = args2;
+#if MPCB_FUSE_LS
+    (void)bs;
+    CK(cudaGraphAddKernelNode(last, g, &n_eval, 1, &kp));
+#else
+    cudaGraphNode_t n_kkt, n_trial;
     CK(cudaGraphAddKernelNode(&n_kkt, g, &n_eval, 1, &kp));
+    kp.kernelParams = args1;
     kp.func = (void*)k_ocp_trial; kp.gridDim = dim3(nblk(nst, bs)); kp.blockDim = dim3(bs);
     CK(cudaGraphAddKernelNode(&n_trial, g, &n_kkt, 1, &kp));
-    void* args2[] = {&a, &n_active};
     kp.func = (void*)k_ocp_accept; kp.gridDim = dim3(nblk((long)h->B * 32, 32 * KKT_WARPS)); kp.blockDim = dim3(32 * KKT_WARPS);
     kp.kernelParams = args2;
     CK(cudaGraphAddKernelNode(last, g, &n_trial, 1, &kp));
+#endif
     return 0;
 }
 
@@ -710,11 +742,16 @@ static int ocp_host_loop(mpcb_ctx* h, OcpArgs& a, double* f, int* status, int* i
     while (ticks < max_ticks) {
         for (int c = 0; c < check_every; ++c) {
             { Prof p(h, s, KC_OCP_EVAL); k_ocp_eval<<<nblk(nst, MPCB_EVAL_BLOCK), MPCB_EVAL_BLOCK, EVAL_SMEM_BYTES, s>>>(a); }
-            { Prof p(h, s, KC_OCP_KKT); k_ocp_kkt<<<KKT_GRID(h->B), 0, s>>>(a); }
+#if MPCB_FUSE_LS
+            if (c == check_every - 1) CK(cudaMemsetAsync(h->n_active, 0, sizeof(int), s));
+            { Prof p(h, s, KC_OCP_KKT); k_ocp_kkt<<<KKT_GRID(h->B), 0, s>>>(a, h->n_active); }
+#else
+            { Prof p(h, s, KC_OCP_KKT); k_ocp_kkt<<<KKT_GRID(h->B), 0, s>>>(a, nullptr); }
             { Prof p(h, s, KC_OCP_TRIAL); k_ocp_trial<<<nblk(nst, bs), bs, 0, s>>>(a); }
             if (c == check_every - 1) CK(cudaMemsetAsync(h->n_active, 0, sizeof(int), s));
             { Prof p(h, s, KC_OCP_ACCEPT); k_ocp_accept<<<nblk((long)h->B * 32, 32 * KKT_WARPS), 32 * KKT_WARPS, 0, s>>>(a, h->n_active); }
-            launches += 4; ticks++;
+#endif
+            launches += TICK_KERNELS; ticks++;
         }
         CK(cudaMemcpyAsync(h->h_active, h->n_active, sizeof(int), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
@@ -1051,7 +1088,7 @@ static void groups_teardown(mpcb_ctx* h) {
         h->host_launches += g->c->host_launches;              // keep the totals of mpcb_total_launches monotone
         unsigned long long ctr[2] = {0, 0};
         cudaMemcpy(ctr, g->c->tick_ctr, sizeof(ctr), cudaMemcpyDeviceToHost);
-        h->host_launches += 4 * (long)ctr[1];
+        h->host_launches += TICK_KERNELS * (long)ctr[1];
         cudaStreamDestroy(g->s); cudaEventDestroy(g->done);
         ocp_graph_drop(g->c);
         cudaFree(g->c->n_active); cudaFreeHost(g->c->h_active); cudaFree(g->c->counters); cudaFree(g->c->tick_ctr);
@@ -1130,11 +1167,11 @@ int mpcb_last_ticks(mpcb_handle_t h) {
 long mpcb_total_launches(mpcb_handle_t h) {
     unsigned long long last = 0, total = 0;
     read_ticks(h, &last, &total);
-    long n = h->host_launches + 4 * (long)total;
+    long n = h->host_launches + TICK_KERNELS * (long)total;
     for (StepGroup* g : h->groups) {
         cudaStreamSynchronize(g->s);
         read_ticks(g->c, &last, &total);
-        n += g->c->host_launches + 4 * (long)total;
+        n += g->c->host_launches + TICK_KERNELS * (long)total;
     }
     return n;
 }

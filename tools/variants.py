@@ -11,12 +11,12 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 VARIANTS = {
-    "eval128x3_r168": "",
-    "eval128x2_r254": "-DMPCB_EVAL_MINBLOCKS=2",
-    "eval64x5_r200": "-DMPCB_EVAL_BLOCK=64 -DMPCB_EVAL_MINBLOCKS=5 -DMPCB_EVAL_MAXNREG=200",
-    "eval32x9_r224": "-DMPCB_EVAL_BLOCK=32 -DMPCB_EVAL_MINBLOCKS=9 -DMPCB_EVAL_MAXNREG=224",
-    "eval32x11_r184": "-DMPCB_EVAL_BLOCK=32 -DMPCB_EVAL_MINBLOCKS=11 -DMPCB_EVAL_MAXNREG=184",
+    "four_kernel_tick (default)": "",
+    "fused_ls": "-DMPCB_FUSE_LS=1",
 }
+# round-2 register/occupancy sweep of k_ocp_eval (profiles/r02_variants_*.txt):
+#   "" (128x3, 168 regs) | -DMPCB_EVAL_MINBLOCKS=2 (254 regs, the default since) |
+#   -DMPCB_EVAL_BLOCK=64 -DMPCB_EVAL_MINBLOCKS=5 -DMPCB_EVAL_MAXNREG=200 | -DMPCB_EVAL_BLOCK=32 -DMPCB_EVAL_MINBLOCKS=9 -DMPCB_EVAL_MAXNREG=224
 
 if __name__ == "__main__":
     mode = sys.argv[1]
