@@ -95,7 +95,12 @@ __global__ void EVAL_BOUNDS k_ocp_eval(OcpArgs a) {
 #ifndef MPCB_FUSE_LS
 #define MPCB_FUSE_LS 0
 #endif
-__global__ void __launch_bounds__(32 * KKT_WARPS) k_ocp_kkt(OcpArgs a, int* n_active) {
+#ifdef MPCB_KKT_MINBLOCKS
+#define KKT_BOUNDS __launch_bounds__(32 * KKT_WARPS, MPCB_KKT_MINBLOCKS)
+#else
+#define KKT_BOUNDS __launch_bounds__(32 * KKT_WARPS)
+#endif
+__global__ void KKT_BOUNDS k_ocp_kkt(OcpArgs a, int* n_active) {
     constexpr int GROUPS = 32 * KKT_WARPS / MPCB_KKT_LANES;        // instances per block
     __shared__ __align__(16) double scratch[GROUPS][KktScratch::total];
     const int inst = (blockIdx.x * blockDim.x + threadIdx.x) / MPCB_KKT_LANES;
