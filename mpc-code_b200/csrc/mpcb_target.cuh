@@ -9,8 +9,20 @@
 #include "mpcb_ocp.cuh"
 
 #define NWS  MPCB_NWSS
-#define MCS  (NX + NY)
-#define NKS  (NWS + MCS)
+// user rows of the target problem (Target_Calc.py:87-109): NGT inequalities g_SS <= 0, each with a slack variable
+// s in (-inf, 0] (g - s = 0, the formulation of IPOPT and of oracle/ipm.py), NHT equalities h_SS = 0
+#ifndef MPCB_NGSS
+#define MPCB_NGSS 0
+#endif
+#ifndef MPCB_NHSS
+#define MPCB_NHSS 0
+#endif
+#define NGT  MPCB_NGSS
+#define NHT  MPCB_NHSS
+#define NOUT (NY + NGT + NHT)          // rows of tgt_out: output map, g_SS, h_SS
+#define NVT  (NWS + NGT)               // variables of the interior-point solve: [xs, us, ys, slacks]
+#define MCS  (NX + NOUT)
+#define NKS  (NVT + MCS)
 #define NWSP (NWS * (NWS + 1) / 2)
 
 // ---------------------------------------------------------------------------------------------
@@ -127,9 +139,9 @@ MPCB_HD void bk_solve(const double* A, const int* ipiv, double* b) {
 #if MPCB_HAS_TARGET
 struct TgtShared { const double *lbx, *ubx; IpmOpts o; };
 
-// constraint values (and derivatives) of the target problem at w = [xs, us, ys]
+// constraint values (and derivatives) of the target problem at v = [xs, us, ys, slacks]; rows [dyn | out | g_SS - s | h_SS]
 MPCB_HD void tgt_eval(const double* w, const double* par, const double* lam, bool derivs,
-                      double* f, double* c, double* grad, double* J /*MCS x NWS col-major*/, double* Hp /*NWSP*/) {
+                      double* f, double* c, double* grad, double* J /*MCS x NVT col-major*/, double* Hp /*NWSP*/) {
     const double* d = par + MPCB_OFFSS_D; const double* px = par + MPCB_OFFSS_PX;
     const double t0 = par[MPCB_OFFSS_T];
     double dl[ND + 1], pxl[NPX + 1];
@@ -140,15 +152,18 @@ MPCB_HD void tgt_eval(const double* w, const double* par, const double* lam, boo
         dyn_value(w, w + NX, dl, pxl, t0, xn);
         for (int i = 0; i < NX; ++i) c[i] = xn[i] - w[i];
         tgt_out(w, par, c + NX);
+        for (int i = 0; i < NGT; ++i) c[NX + NY + i] -= w[NWS + i];
         tgt_cost(w, par, f);
         return;
     }
-    double A[NX * NX], Bm[NX * NU], Hd[NZP], Hc[NWSP], Ho[NWSP], Jo[NY * NWS];
+    double A[NX * NX], Bm[NX * NU], Hd[NZP], Hc[NWSP], Ho[NWSP], Jo[NOUT * NWS];
     for (int i = 0; i < NZP; ++i) Hd[i] = 0.0;
     dyn_full(w, w + NX, dl, pxl, t0, lam, xn, A, Bm, Hd);
     for (int i = 0; i < NX; ++i) c[i] = xn[i] - w[i];
     tgt_out_d(w, par, lam + NX, c + NX, Jo, Ho);
+    for (int i = 0; i < NGT; ++i) c[NX + NY + i] -= w[NWS + i];
     tgt_cost_d(w, par, f, grad, Hc);
+    for (int i = 0; i < NGT; ++i) grad[NWS + i] = 0.0;
     for (int i = 0; i < NWSP; ++i) Hp[i] = Hc[i] + Ho[i];
     for (int i = 0; i < NZP; ++i) Hp[i] += Hd[i];            // (xs,us) block leads the packed triangle
     for (int j = 0; j < NWS; ++j) {
@@ -158,8 +173,10 @@ MPCB_HD void tgt_eval(const double* w, const double* par, const double* lam, boo
             else if (j < NZ) v = Bm[i + NX * (j - NX)];
             J[i + MCS * j] = v;
         }
-        for (int i = 0; i < NY; ++i) J[NX + i + MCS * j] = Jo[i + NY * j];
+        for (int i = 0; i < NOUT; ++i) J[NX + i + MCS * j] = Jo[i + NOUT * j];
     }
+    for (int j = 0; j < NGT; ++j)                            // slack columns
+        for (int i = 0; i < MCS; ++i) J[i + MCS * (NWS + j)] = (i == NX + NY + j) ? -1.0 : 0.0;
 }
 
 // Whole interior-point solve of one target problem (same algorithm as oracle/ipm.py and mpcb_ocp.cuh).
@@ -168,25 +185,34 @@ MPCB_HD void tgt_eval(const double* w, const double* par, const double* lam, boo
 // the restoration out of the common variant halves its register spills (ptxas: 520 / 1288 B vs 1132 / 1930 B).
 #define TGT_NEEDS_RESTO 1000
 template <bool MPCB_TGT_RESTO>
-MPCB_HD void tgt_solve_t(const double* par, double* w, double* fout, int* status_out, int* iters_out, const TgtShared& S) {
+MPCB_HD void tgt_solve_t(const double* par, double* w_io, double* fout, int* status_out, int* iters_out, const TgtShared& S) {
     const IpmOpts& o = S.o;
     const double rf = o.bound_relax;
-    double lo[NWS], hi[NWS]; bool hl[NWS], hu[NWS];
+    double w[NVT], lo[NVT], hi[NVT]; bool hl[NVT], hu[NVT];
     int nb = 0;
     for (int i = 0; i < NWS; ++i) {
         hl[i] = fin(S.lbx[i]); hu[i] = fin(S.ubx[i]);
         lo[i] = hl[i] ? rlo(S.lbx[i], rf) : S.lbx[i];
         hi[i] = hu[i] ? rhi(S.ubx[i], rf) : S.ubx[i];
         nb += (hl[i] ? 1 : 0) + (hu[i] ? 1 : 0);
-        w[i] = push_in(w[i], lo[i], hi[i], o.bound_push);
+        w[i] = push_in(w_io[i], lo[i], hi[i], o.bound_push);
     }
-    double y[MCS], zL[NWS], zU[NWS];
+    if (NGT > 0) {                      // slacks start at g_SS(pushed point), pushed into (-inf, 0] (oracle/ipm.py: starting point)
+        double f0, c0[MCS];
+        for (int i = NWS; i < NVT; ++i) w[i] = 0.0;
+        tgt_eval(w, par, nullptr, false, &f0, c0, nullptr, nullptr, nullptr);
+        for (int i = NWS; i < NVT; ++i) {
+            hl[i] = false; hu[i] = true; lo[i] = -INFINITY; hi[i] = rhi(0.0, rf); nb += 1;
+            w[i] = push_in(c0[NX + NY + (i - NWS)], lo[i], hi[i], o.bound_push);
+        }
+    }
+    double y[MCS], zL[NVT], zU[NVT];
     for (int i = 0; i < MCS; ++i) y[i] = 0.0;
-    for (int i = 0; i < NWS; ++i) { zL[i] = hl[i] ? 1.0 : 0.0; zU[i] = hu[i] ? 1.0 : 0.0; }
+    for (int i = 0; i < NVT; ++i) { zL[i] = hl[i] ? 1.0 : 0.0; zU[i] = hu[i] ? 1.0 : 0.0; }
     double mu = o.mu_init, tau = fmax(0.99, 1.0 - mu), dw_last = 0.0, theta0 = -1.0;
     double filt[2 * MPCB_MAXFILT]; int nfilt = 0, acc = 0, it = 0, status = -1;
     bool resto = false; int resto_calls = 0; double theta_entry = 0.0;      // feasibility restoration, as in ocp_accept
-    double f = 0.0, c[MCS], grad[NWS], J[MCS * NWS], Hp[NWSP];
+    double f = 0.0, c[MCS], grad[NVT], J[MCS * NVT], Hp[NWSP];
     bool evaluate = true;               // ONE call site of the derivative evaluation (three inlined RK4 sweeps): the solver's
     while (true) {                      // code is 240 kB otherwise and a sixth of its stalls are instruction fetches
         if (evaluate) tgt_eval(w, par, y, true, &f, c, grad, J, Hp);
@@ -194,12 +220,12 @@ MPCB_HD void tgt_solve_t(const double* par, double* w, double* fout, int* status
         if (it == 0 && !resto) {        // IPOPT: a starting point whose functions do not evaluate ends the solve with -13
             double chk = f;
             for (int i = 0; i < MCS; ++i) chk += c[i];
-            for (int i = 0; i < NWS; ++i) chk += grad[i];
+            for (int i = 0; i < NVT; ++i) chk += grad[i];
             if (!(chk == chk) || !fin(chk)) { status = -13; break; }
         }
         // optimality error
         double dual = 0.0, prim = 0.0, ysum = 0.0, zsum = 0.0, c0 = 0.0;
-        for (int j = 0; j < NWS; ++j) {
+        for (int j = 0; j < NVT; ++j) {
             double r = grad[j] - zL[j] + zU[j];
             for (int i = 0; i < MCS; ++i) r += J[i + MCS * j] * y[i];
             dual = fmax(dual, fabs(r));
@@ -224,7 +250,7 @@ MPCB_HD void tgt_solve_t(const double* par, double* w, double* fout, int* status
         bool changed = false;
         while (!resto && mu > mu_min) {
             double cm = 0.0;
-            for (int j = 0; j < NWS; ++j) {
+            for (int j = 0; j < NVT; ++j) {
                 if (hl[j]) cm = fmax(cm, fabs((w[j] - lo[j]) * zL[j] - mu));
                 if (hu[j]) cm = fmax(cm, fabs((hi[j] - w[j]) * zU[j] - mu));
             }
@@ -238,8 +264,8 @@ MPCB_HD void tgt_solve_t(const double* par, double* w, double* fout, int* status
         double dwreg = 0.0, dcreg = 0.0; bool first = true, ok = false;
         for (int attempt = 0; attempt < 60; ++attempt) {
             for (int i = 0; i < NKS * NKS; ++i) K[i] = 0.0;
-            for (int j = 0; j < NWS; ++j) {
-                for (int i = j; i < NWS; ++i) K[i + NKS * j] = resto ? 0.0 : Hp[tri(i, j)];
+            for (int j = 0; j < NVT; ++j) {
+                if (j < NWS) for (int i = j; i < NWS; ++i) K[i + NKS * j] = resto ? 0.0 : Hp[tri(i, j)];
                 double sig = dwreg;
                 if (resto) {             // proximal Gauss-Newton step: zeta D_R^2 + primal barrier Hessian
                     const double sc = fmax(1.0, fabs(w[j]));
@@ -251,12 +277,12 @@ MPCB_HD void tgt_solve_t(const double* par, double* w, double* fout, int* status
                     if (hu[j]) sig += zU[j] / (hi[j] - w[j]);
                 }
                 K[j + NKS * j] += sig;
-                for (int i = 0; i < MCS; ++i) K[NWS + i + NKS * j] = J[i + MCS * j];
+                for (int i = 0; i < MCS; ++i) K[NVT + i + NKS * j] = J[i + MCS * j];
             }
-            for (int i = 0; i < MCS; ++i) K[NWS + i + NKS * (NWS + i)] = -dcreg;
+            for (int i = 0; i < MCS; ++i) K[NVT + i + NKS * (NVT + i)] = -dcreg;
             int np_, nn_, nz_;
             bk_factor<NKS>(K, ipiv, &np_, &nn_, &nz_);
-            if (np_ == NWS && nn_ == MCS && nz_ == 0) { ok = true; break; }
+            if (np_ == NVT && nn_ == MCS && nz_ == 0) { ok = true; break; }
             if (nz_ > 0) dcreg = 1e-8 * pow(mu, 0.25);
             if (first) { dwreg = (dw_last == 0.0) ? 1e-4 : fmax(1e-20, dw_last / 3.0); first = false; }
             else dwreg *= (dw_last == 0.0) ? 100.0 : 8.0;
@@ -264,7 +290,7 @@ MPCB_HD void tgt_solve_t(const double* par, double* w, double* fout, int* status
         }
         if (!ok) { status = -3; break; }
         if (dwreg > 0.0) dw_last = dwreg;
-        for (int j = 0; j < NWS; ++j) {
+        for (int j = 0; j < NVT; ++j) {
             double r = grad[j];
             for (int i = 0; i < MCS; ++i) r += J[i + MCS * j] * y[i];
             if (resto) r = 0.0;
@@ -272,12 +298,12 @@ MPCB_HD void tgt_solve_t(const double* par, double* w, double* fout, int* status
             if (hu[j]) r += mu / (hi[j] - w[j]);
             rhs[j] = -r;
         }
-        for (int i = 0; i < MCS; ++i) rhs[NWS + i] = -c[i];
+        for (int i = 0; i < MCS; ++i) rhs[NVT + i] = -c[i];
         bk_solve<NKS>(K, ipiv, rhs);
         // step sizes, barrier objective
         double amax = 1.0, az = 1.0, gphid = 0.0, barr = 0.0, theta = 0.0;
-        double dzL[NWS], dzU[NWS];
-        for (int j = 0; j < NWS; ++j) {
+        double dzL[NVT], dzU[NVT];
+        for (int j = 0; j < NVT; ++j) {
             const double dv = rhs[j];
             gphid += grad[j] * dv;
             dzL[j] = dzU[j] = 0.0;
@@ -306,11 +332,11 @@ MPCB_HD void tgt_solve_t(const double* par, double* w, double* fout, int* status
         else amin = 1e-5;
         amin *= 0.05;
         double alpha = amax; bool accepted = false, ftype = false;
-        double wt[NWS], ft, ct[MCS];
+        double wt[NVT], ft, ct[MCS];
         if (MPCB_TGT_RESTO && resto) {  // restoration iteration: Armijo on the violation alone
             double th_t = 0.0;
             while (alpha > 1e-5) {         // shorter: jammed against the bounds / no descent -> the violation cannot be reduced
-                for (int j = 0; j < NWS; ++j) wt[j] = w[j] + alpha * rhs[j];
+                for (int j = 0; j < NVT; ++j) wt[j] = w[j] + alpha * rhs[j];
                 tgt_eval(wt, par, y, false, &ft, ct, nullptr, nullptr, nullptr);
                 th_t = 0.0;
                 for (int i = 0; i < MCS; ++i) th_t += fabs(ct[i]);
@@ -319,7 +345,7 @@ MPCB_HD void tgt_solve_t(const double* par, double* w, double* fout, int* status
             }
             if (!accepted) { status = theta > 1e-4 ? 2 : -2; break; }
             double b_t = 0.0;
-            for (int j = 0; j < NWS; ++j) {
+            for (int j = 0; j < NVT; ++j) {
                 w[j] = wt[j];
                 if (hl[j]) { const double d = w[j] - lo[j]; zL[j] = mu / d; b_t += log(d); }
                 if (hu[j]) { const double d = hi[j] - w[j]; zU[j] = mu / d; b_t += log(d); }
@@ -334,11 +360,11 @@ MPCB_HD void tgt_solve_t(const double* par, double* w, double* fout, int* status
             continue;
         }
         while (alpha >= amin * (1.0 - 1e-12) && alpha > 1e-16) {
-            for (int j = 0; j < NWS; ++j) wt[j] = w[j] + alpha * rhs[j];
+            for (int j = 0; j < NVT; ++j) wt[j] = w[j] + alpha * rhs[j];
             tgt_eval(wt, par, y, false, &ft, ct, nullptr, nullptr, nullptr);
             double th_t = 0.0, b_t = 0.0;
             for (int i = 0; i < MCS; ++i) th_t += fabs(ct[i]);
-            for (int j = 0; j < NWS; ++j) { if (hl[j]) b_t += log(wt[j] - lo[j]); if (hu[j]) b_t += log(hi[j] - wt[j]); }
+            for (int j = 0; j < NVT; ++j) { if (hl[j]) b_t += log(wt[j] - lo[j]); if (hu[j]) b_t += log(hi[j] - wt[j]); }
             const double ph_t = ft - mu * b_t;
             bool okk = (th_t == th_t) && (ph_t == ph_t) && fin(th_t) && fin(ph_t) && th_t <= theta_max;
             if (okk) for (int i = 0; i < nfilt; ++i) if (th_t >= filt[2 * i] && ph_t >= filt[2 * i + 1]) { okk = false; break; }
@@ -359,12 +385,12 @@ MPCB_HD void tgt_solve_t(const double* par, double* w, double* fout, int* status
             continue;
         }
         if (!ftype && nfilt < MPCB_MAXFILT) { filt[2 * nfilt] = (1.0 - 1e-5) * theta; filt[2 * nfilt + 1] = phi - 1e-8 * theta; nfilt++; }
-        for (int j = 0; j < NWS; ++j) {
+        for (int j = 0; j < NVT; ++j) {
             w[j] = wt[j];
             if (hl[j]) { const double dn = w[j] - lo[j]; zL[j] = fmax(fmin(zL[j] + az * dzL[j], 1e10 * mu / dn), mu / (1e10 * dn)); }
             if (hu[j]) { const double dn = hi[j] - w[j]; zU[j] = fmax(fmin(zU[j] + az * dzU[j], 1e10 * mu / dn), mu / (1e10 * dn)); }
         }
-        for (int i = 0; i < MCS; ++i) y[i] += alpha * rhs[NWS + i];
+        for (int i = 0; i < MCS; ++i) y[i] += alpha * rhs[NVT + i];
         it += 1;
         evaluate = true;
     }
@@ -373,6 +399,7 @@ MPCB_HD void tgt_solve_t(const double* par, double* w, double* fout, int* status
         double ct[MCS];
         tgt_eval(w, par, y, false, &f, ct, nullptr, nullptr, nullptr);
     }
+    for (int j = 0; j < NWS; ++j) w_io[j] = w[j];
     *fout = f; *status_out = status; *iters_out = it;
 }
 

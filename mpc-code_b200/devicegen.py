@@ -282,15 +282,21 @@ def generate_header(prob, ss_spec, ocp_spec, opts: Optional[Dict] = None) -> Dic
     # ---- target problem (Target_Calc.py:75-124) ------------------------------
     if ss_spec is not None:
         t_ = ss_spec
-        D.update(MPCB_HAS_TARGET=1, MPCB_NWSS=t_.nw, MPCB_NPARSS=t_.npar)
+        D.update(MPCB_HAS_TARGET=1, MPCB_NWSS=t_.nw, MPCB_NPARSS=t_.npar, MPCB_NGSS=t_.ng_ss, MPCB_NHSS=t_.nh_ss)
         for k_, v_ in t_.off.items():
             D["MPCB_OFFSS_%s" % k_.upper()] = v_
         w, par = t_.wss, t_.par
         Hf, gf = hessian(t_.cost, w)
         fns.append(CFunction("tgt_cost", [("w", w), ("par", par)], [("f", t_.cost)]))
         fns.append(CFunction("tgt_cost_d", [("w", w), ("par", par)], [("f", t_.cost), ("g", gf), ("H", tril_pack(Hf))]))
-        mult = SX.sym("mult", t_.p)
+        # rows after the model equalities: output map, then the user rows g_SS <= 0 and h_SS = 0 (Target_Calc.py:80-109)
         yres = t_.Ynext - t_.Ys
+        if t_.Gss is not None:
+            yres = vertcat(yres, t_.Gss)
+        if t_.Hss is not None:
+            yres = vertcat(yres, t_.Hss)
+        yres = SX(yres)
+        mult = SX.sym("mult", yres.numel())
         Hy, _ = hessian(mtimes(mult.T, yres), w)
         fns.append(CFunction("tgt_out", [("w", w), ("par", par)], [("r", yres)]))
         fns.append(CFunction("tgt_out_d", [("w", w), ("par", par), ("mult", mult)],

@@ -278,7 +278,8 @@ def make_specs(prob: MpcProblem):
         return None, None
     s, b = prob.sym, prob.bounds_ss
     ss = build_target_spec(prob.nx, prob.nu, prob.ny, prob.nd, prob.npx, prob.npy, prob.Fx_model, prob.Fy_model,
-                           prob.Fss_obj, prob.flags["QForm_ss"], prob.flags["DUssForm"], prob.sol_optss, None, None,
+                           prob.Fss_obj, prob.flags["QForm_ss"], prob.flags["DUssForm"], prob.sol_optss,
+                           prob.ns.get("User_g_ineq_SS"), prob.ns.get("User_h_eq_SS"),
                            umin=b["umin"], umax=b["umax"], w_s=None, z_s=None, ymin=b["ymin"], ymax=b["ymax"],
                            xmin=b["xmin"], xmax=b["xmax"], h=prob.h)
     b = prob.bounds_dyn
@@ -286,9 +287,9 @@ def make_specs(prob: MpcProblem):
     if "User_fobj_Cont" in prob.ns:
         extra = dict(fx=prob.ns["User_fxm_Cont"], xstat=s["xs"], ustat=s["us"])
     f = prob.flags
-    for name in ("User_h_eq", "User_g_ineq_SS", "User_h_eq_SS"):
-        if prob.ns.get(name) is not None:
-            raise NotImplementedError("%s is outside the accelerated path (stage inequalities User_g_ineq are supported)" % name)
+    if prob.ns.get("User_h_eq") is not None:
+        raise NotImplementedError("User_h_eq is outside the accelerated path (User_g_ineq, User_g_ineq_SS and "
+                                  "User_h_eq_SS are supported)")
     ocp = build_ocp_spec(s["x"], s["u"], s["y"], s["d"], s["t"], s["px"], s["py"], prob.nx, prob.nu, prob.ny, prob.nd,
                          prob.npx, prob.npy, 0, 0, prob.Fx_model, prob.Fy_model, prob.F_obj, prob.Vfin, prob.N,
                          f["QForm"], f["DUForm"], f["DUFormEcon"], f["ContForm"], f["TermCons"], False, True, True,

@@ -356,8 +356,9 @@ class BatchedNlpSolver:
                 return np.hstack(blocks).reshape(-1) if blocks else np.zeros(0)
             h.set_const("ocp_lbg", per_stage(lbg)); h.set_const("ocp_ubg", per_stage(ubg))
         else:
-            if np.any(lbg != 0.0) or np.any(ubg != 0.0):
-                raise ValueError("the target problem's g rows are equalities (lbg = ubg = 0)")
+            if not (np.array_equal(lbg, s.g_lb) and np.array_equal(ubg, s.g_ub)):
+                raise ValueError("the target problem's g bounds are fixed by its construction (Target_Calc.py:146-150): "
+                                 "equalities, and -inf <= g_SS <= 0 for the user inequality rows")
             h.set_const("ss_lbx", lbx); h.set_const("ss_ubx", ubx)
         self._bounds_key = key
 

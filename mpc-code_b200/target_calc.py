@@ -1,7 +1,8 @@
 """``opt_ss``: the steady-state target problem (``Target_Calc.py:20-161``).
 
 Variables ``wss = [Xs, Us, Ys]``; parameters ``par_ss = [usp|ysp|xsp|d|Us_prev|vec(lam)|t|px|py]``;
-equalities ``Fx_model(Xs,Us,h,d,t,px) - Xs = 0`` and ``Fy_model(Xs,Us,d,t,py) + lam (Us - Us_prev) - Ys = 0``;
+equalities ``Fx_model(Xs,Us,h,d,t,px) - Xs = 0`` and ``Fy_model(Xs,Us,d,t,py) + lam (Us - Us_prev) - Ys = 0``,
+then the user rows ``User_g_ineq_SS(xs,us,ys,d,t,px,py) <= 0`` and ``User_h_eq_SS(...) = 0`` (``:87-109,149-153``);
 box bounds on all three blocks.  Recorded symbolically in `TargetSpec`.
 """
 from __future__ import annotations
@@ -11,7 +12,7 @@ from typing import Any, Dict
 
 import numpy as np
 
-from .sx import SX, Function, mtimes
+from .sx import SX, Function, mtimes, vertcat
 
 
 @dataclass
@@ -28,6 +29,9 @@ class TargetSpec:
     flags: Dict[str, Any]
     w_lb: np.ndarray; w_ub: np.ndarray; g_lb: np.ndarray; g_ub: np.ndarray
     sol_opts: Dict[str, Any] = field(default_factory=dict)
+    Gss: Any = None      # User_g_ineq_SS(Xs,Us,Ys,d,t,px,py) <= 0   (:87-98), SX column or None
+    Hss: Any = None      # User_h_eq_SS(...) = 0                     (:91-103)
+    ng_ss: int = 0; nh_ss: int = 0
 
 
 def par_ss_offsets(n, m, p, nd, npx, npy) -> Dict[str, int]:
@@ -47,8 +51,6 @@ def _inf_or(v, n, sign):
 def build_target_spec(n, m, p, nd, npx, npy, Fx_model, Fy_model, Fss_obj, QForm_ss, DUssForm, sol_opts,
                       G_ineq_SS, H_eq_SS, umin=None, umax=None, w_s=None, z_s=None, ymin=None, ymax=None,
                       xmin=None, xmax=None, h=None) -> TargetSpec:
-    if G_ineq_SS is not None or H_eq_SS is not None:
-        raise NotImplementedError("user g/h constraints on the target problem are outside the accelerated path")
     nxu, nxuy = n + m, n + m + p
     off = par_ss_offsets(n, m, p, nd, npx, npy)
     wss = SX.sym("wss", nxuy)
@@ -75,8 +77,16 @@ def build_target_spec(n, m, p, nd, npx, npy, Fx_model, Fy_model, Fss_obj, QForm_
     cost = Fss_obj(dx, du, dy, xsp, usp, ysp)
     w_lb = np.concatenate([_inf_or(xmin, n, -1), _inf_or(umin, m, -1), _inf_or(ymin, p, -1)])
     w_ub = np.concatenate([_inf_or(xmax, n, +1), _inf_or(umax, m, +1), _inf_or(ymax, p, +1)])
-    g_lb = np.zeros(n + p); g_ub = np.zeros(n + p)
-    return TargetSpec(n=n, m=m, p=p, nd=nd, npx=npx, npy=npy, h=float(h), nw=nxuy, npar=off["end"], off=off,
+    Gss = Hss = None
+    if G_ineq_SS is not None:
+        Gss = SX(vertcat(G_ineq_SS(Xs, Us, Ys, d, t, px, py)))
+    if H_eq_SS is not None:
+        Hss = SX(vertcat(H_eq_SS(Xs, Us, Ys, d, t, px, py)))
+    ng1 = 0 if Gss is None else Gss.numel()
+    ng2 = 0 if Hss is None else Hss.numel()
+    g_lb = np.zeros(n + p + ng1 + ng2); g_ub = np.zeros(n + p + ng1 + ng2)
+    g_lb[n + p:n + p + ng1] = -np.inf                                   # (:149-150)
+    return TargetSpec(Gss=Gss, Hss=Hss, ng_ss=ng1, nh_ss=ng2, n=n, m=m, p=p, nd=nd, npx=npx, npy=npy, h=float(h), nw=nxuy, npar=off["end"], off=off,
                       wss=wss, par=par, Xs=Xs, Us=Us, Ys=Ys, Xnext=SX(Xnext), Ynext=SX(Ynext), cost=SX(cost),
                       Fx_model=Fx_model, Fy_model=Fy_model, flags=dict(QForm_ss=QForm_ss, DUssForm=DUssForm),
                       w_lb=w_lb, w_ub=w_ub, g_lb=g_lb, g_ub=g_ub, sol_opts=dict(sol_opts or {}))

@@ -66,6 +66,9 @@ def target_functions(spec):
     """Target-problem maps (``Target_Calc.py:75-124``)."""
     w, par = spec.wss, spec.par
     con = vertcat(spec.Xnext - spec.Xs, spec.Ynext - spec.Ys)
+    for extra in (getattr(spec, "Gss", None), getattr(spec, "Hss", None)):      # user rows (Target_Calc.py:87-109)
+        if extra is not None:
+            con = vertcat(con, extra)
     mult = SX.sym("mult", con.numel())
     Hc, _ = _scalar_hess(mtimes(mult.T, con), w)
     Hf, gf = _scalar_hess(spec.cost, w)
