@@ -11,11 +11,9 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 VARIANTS = {
-    "kkt_72regs_28w (default)": "",
-    "kkt_118regs_16w": "-DMPCB_KKT_MINBLOCKS=1",
-    "kkt_96regs_20w": "-DMPCB_KKT_MINBLOCKS=5",
-    "kkt_80regs_24w": "-DMPCB_KKT_MINBLOCKS=6",
+    "default": "",
 }
+# KKT kernel occupancy (profiles/r02_variants_kktocc.txt): "-DMPCB_KKT_MINBLOCKS=1" (118 regs) | "=5" (96) | "=6" (80)
 # line search fused into the KKT warp: "-DMPCB_FUSE_LS=1" (profiles/r02_variants_fuse.txt)
 # round-2 register/occupancy sweep of k_ocp_eval (profiles/r02_variants_*.txt):
 #   "" (128x3, 168 regs) | -DMPCB_EVAL_MINBLOCKS=2 (254 regs, the default since) |
