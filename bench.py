@@ -121,13 +121,13 @@ class OraclePool:
         self.pool.close(); self.pool.join()
 
 
-def cpu_baselines(cores, cxx_inst_per_core=8, cxx_steps=40, numpy_steps=20):
-    """The two CPU figures of one bench line (bounded: ~10 s of C++ work, ~10 s of NumPy work)."""
+def cpu_baselines(cores, cxx_inst_per_core=16, cxx_steps=60, numpy_steps=20):
+    """The two CPU figures of one bench line (bounded: ~30 core-seconds of C++ work, ~70 core-seconds of NumPy work)."""
     v, threads, wall = cxx_throughput(cxx_inst_per_core * cores, cxx_steps)
     cxx = {"value": v, "unit": "steps/s", "cores": threads, "kind": "port",
            "sample": "%d instances x %d consecutive closed-loop steps after %d cold-start steps each, same workload; host build of "
-                     "this repo's solver sources (same algorithm, C++, g++ -O3 -fopenmp over instances; %.1f s); not IPOPT"
-                     % (cxx_inst_per_core * cores, cxx_steps, CPU_WARM_STEPS, wall)}
+                     "this repo's solver sources (same algorithm, C++, g++ -O3 -fopenmp over instances; %.1f s wall = %.0f core-seconds); "
+                     "not IPOPT" % (cxx_inst_per_core * cores, cxx_steps, CPU_WARM_STEPS, wall, wall * threads)}
     pool = OraclePool(cores)
     v2, wall2 = pool.throughput(cores, numpy_steps)
     pool.close()
