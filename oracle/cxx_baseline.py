@@ -67,6 +67,13 @@ class CxxLoop:
         self.lib.cxx_closed_loop.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_double] + [VP] * 13 + [ctypes.c_int] + \
             [VP] * 5 + [ctypes.c_int] * 3 + [VP] * 3 + [ctypes.c_int, VP]
         self.lbg, self.ubg = [np.ascontiguousarray(v if v.size else np.zeros(1), dtype=float) for v in range_bounds]
+        # every core this process may run on, whatever OMP_NUM_THREADS says (torchrun sets it to 1 for its workers)
+        try:
+            ncpu = len(os.sched_getaffinity(0))
+        except AttributeError:
+            ncpu = os.cpu_count() or 1
+        self.lib.cxx_set_threads.argtypes = [ctypes.c_int]
+        self.lib.cxx_set_threads(int(os.environ.get("MPCB_CPU_THREADS", ncpu)))
 
     def threads(self):
         return int(self.lib.cxx_threads())

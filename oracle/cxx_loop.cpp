@@ -41,6 +41,15 @@ static void solve_ocp(OcpInst& I, const OcpShared& S, double* scratch, int max_i
 
 extern "C" {
 
+// Launchers (torch.distributed.run) export OMP_NUM_THREADS=1 to their workers: the CPU arm sets its thread count itself.
+void cxx_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int cxx_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();
