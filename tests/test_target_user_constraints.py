@@ -130,3 +130,27 @@ def test_gpu_closed_loop_matches_oracle(ssu):
     assert np.abs(sol["x"].cpu().numpy() - r.x).max() < 1e-9 * np.abs(r.x).max()
     with pytest.raises(ValueError):                       # the user rows' bounds are part of the problem's construction
         ctl.solver_ss(lbx=ss.w_lb, ubx=ss.w_ub, x0=w0, p=par, lbg=np.zeros_like(ss.g_lb), ubg=ss.g_ub)
+
+
+def test_infeasible_user_constraint_is_reported_like_the_oracle(tmp_path, ssu):
+    """A duty limit no point inside the bounds can meet: restoration ends at a stationary point of the violation, status 2
+    (Infeasible_Problem_Detected, the status `MPC_code.py:714` gates the target on) from the oracle and the device code alike."""
+    import os
+    import __graft_entry__ as entry
+    from conftest import Bundle, ROOT
+    from oracle.nlp import TargetNlp
+    src = open(os.path.join(ROOT, "examples", "nmpc_cstr_ss_user.py")).read()
+    assert "- 15.9)" in src
+    src = src.replace("- 15.9)", "- 1.0)").replace("os.path.dirname(__file__)", repr(os.path.join(ROOT, "examples")))
+    path = tmp_path / "nmpc_cstr_ss_infeas.py"
+    path.write_text(src)
+    entry.EXAMPLES["nmpc_cstr_ss_infeas"] = str(path)
+    try:
+        b = Bundle("nmpc_cstr_ss_infeas")
+        par, w0 = _par(b), _guess(b)
+        r = TargetNlp(b.ss, b.oracle).solve(w0, par)
+        w, f, st, it = b.harness_target(par, w0)
+    finally:
+        entry.EXAMPLES.pop("nmpc_cstr_ss_infeas", None)
+    assert r.status == 2 and st[0] == 2 and it[0] == r.iters
+    assert np.abs(w[0] - r.x).max() < 1e-8 * np.abs(r.x).max()
