@@ -76,6 +76,19 @@ __global__ void EVAL_BOUNDS k_ocp_eval(OcpArgs a) {
     ocp_eval_stage<MPCB_EVAL_SMEM>(I, a.S, k, RkBuf{eval_smem + threadIdx.x, MPCB_EVAL_BLOCK});
 }
 
+#if MPCB_EVAL_FIRST
+// first tick of a solve: all multipliers are zero (see ocp_eval_stage<., FIRST>)
+__global__ void __launch_bounds__(128) k_ocp_eval_first(OcpArgs a) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int inst = tid / NH, k = tid % NH;
+    if (inst >= a.B) return;
+    if (a.st[inst].state != ST_EVAL) return;
+    if (k == 0) atomicAdd(a.counters, 1ULL);
+    OcpInst I = ocp_view(a, inst);
+    ocp_eval_stage<false, true>(I, a.S, k);
+}
+#endif
+
 // KKT step: one thread per instance (small stage blocks, MPCB_KKT_LANES == 1) or one warp per instance with
 // per-warp scratch in shared memory (MPCB_KKT_LANES == 32)
 #ifndef MPCB_TGT_BLOCK
@@ -641,7 +654,8 @@ static bool same_opts(const mpcb_opts_t& a, const mpcb_opts_t& b) {
 // instances are all done is four kernels that exit at once.  U = MPCB_GRAPH_UNROLL (environment), default 10: a warm
 // closed-loop step of Ex_NMPC needs 11-13 ticks.
 #define TICK_KERNELS (MPCB_FUSE_LS ? 2 : 4)
-static int add_tick(mpcb_ctx* h, cudaGraph_t g, cudaGraphNode_t* dep, int ndep, OcpArgs& a, int* n_active, cudaGraphNode_t* last) {
+static int add_tick(mpcb_ctx* h, cudaGraph_t g, cudaGraphNode_t* dep, int ndep, OcpArgs& a, int* n_active, cudaGraphNode_t* last,
+                    bool first = false) {
     const int bs = 128;
     const long nst = (long)h->B * NH;
     cudaKernelNodeParams kp; memset(&kp, 0, sizeof(kp));
@@ -650,6 +664,11 @@ static int add_tick(mpcb_ctx* h, cudaGraph_t g, cudaGraphNode_t* dep, int ndep, 
     kp.kernelParams = args1;
     kp.func = (void*)k_ocp_eval; kp.gridDim = dim3(nblk(nst, MPCB_EVAL_BLOCK)); kp.blockDim = dim3(MPCB_EVAL_BLOCK);
     kp.sharedMemBytes = (unsigned)EVAL_SMEM_BYTES;
+#if MPCB_EVAL_FIRST
+    if (first) { kp.func = (void*)k_ocp_eval_first; kp.gridDim = dim3(nblk(nst, 128)); kp.blockDim = dim3(128); kp.sharedMemBytes = 0; }
+#else
+    (void)first;
+#endif
     CK(cudaGraphAddKernelNode(&n_eval, g, dep, ndep, &kp));
     kp.sharedMemBytes = 0;
     { dim3 gk(1), bk(1); auto set = [&](int gx, int bx) { gk = dim3(gx); bk = dim3(bx); }; set(KKT_GRID(h->B));
@@ -698,7 +717,7 @@ static int ocp_graph_build(mpcb_ctx* h, const OcpArgs& a_in, double* f, int* sta
     int* n_active = h->n_active; int* no_count = nullptr;
     for (int t = 0; t < unroll; ++t) {                                   // only the last unrolled tick counts the active instances
         cudaGraphNode_t last;
-        int rc = add_tick(h, g, &prev, 1, a, (t == unroll - 1) ? n_active : no_count, &last);
+        int rc = add_tick(h, g, &prev, 1, a, (t == unroll - 1) ? n_active : no_count, &last, t == 0);
         if (rc) return rc;
         prev = last;
     }
@@ -746,6 +765,10 @@ static int ocp_host_loop(mpcb_ctx* h, OcpArgs& a, double* f, int* status, int* i
     const int check_every = 2;
     while (ticks < max_ticks) {
         for (int c = 0; c < check_every; ++c) {
+#if MPCB_EVAL_FIRST
+            if (ticks == 0) { Prof p(h, s, KC_OCP_EVAL); k_ocp_eval_first<<<nblk(nst, 128), 128, 0, s>>>(a); }
+            else
+#endif
             { Prof p(h, s, KC_OCP_EVAL); k_ocp_eval<<<nblk(nst, MPCB_EVAL_BLOCK), MPCB_EVAL_BLOCK, EVAL_SMEM_BYTES, s>>>(a); }
 #if MPCB_FUSE_LS
             if (c == check_every - 1) CK(cudaMemsetAsync(h->n_active, 0, sizeof(int), s));

@@ -303,7 +303,14 @@ MPCB_HD void bound_terms(double v, double lo, double hi, double zl, double zu, d
 #define EVAL_RK_DOUBLES 0
 #endif
 
-template <bool EXT = false>
+// FIRST: the evaluation that follows ocp_init_stage.  Every multiplier is zero there, so the Hessian of the Lagrangian is
+// the cost Hessian alone and the adjoint / second-order RK4 sweeps would only add exact zeros: the dynamics are
+// differentiated to first order (dyn_sens, one forward sweep, no sub-step records).  RK4 models with a separate stage
+// cost only (the quadrature form integrates the cost with the adjoint seed 1).
+#ifndef MPCB_EVAL_FIRST
+#define MPCB_EVAL_FIRST (MPCB_DYN_RK4 && !MPCB_CONTFORM && !MPCB_DENSE_SH)
+#endif
+template <bool EXT = false, bool FIRST = false>
 MPCB_HD void ocp_eval_stage(OcpInst& I, const OcpShared& S, int k, RkBuf rb = RkBuf{nullptr, 1}) {
     const double* w = I.w;
     const double rf = S.o.bound_relax;
@@ -345,13 +352,15 @@ MPCB_UNROLL
         for (int i = 0; i < NX; ++i) xn[i] = xe[i];
     }
 #elif NAUG == 0
-    dyn_full<EXT>(z, u, d, px, t0, lam, xn, A, Bm, Hp, rb);
+    if constexpr (FIRST) dyn_sens(z, u, d, px, t0, xn, A, Bm);
+    else dyn_full<EXT>(z, u, d, px, t0, lam, xn, A, Bm, Hp, rb);
 #else
     {   // model part by the RK4 sweeps, then embedded into the augmented stage:  z+ = [Fx(x,u); u]
         double xm[NX], Am[NX * NX], Bmm[NX * NU], Hm[NZP];
 MPCB_UNROLL
         for (int i = 0; i < NZP; ++i) Hm[i] = 0.0;
-        dyn_full<EXT>(z, u, d, px, t0, lam, xm, Am, Bmm, Hm, rb);
+        if constexpr (FIRST) dyn_sens(z, u, d, px, t0, xm, Am, Bmm);
+        else dyn_full<EXT>(z, u, d, px, t0, lam, xm, Am, Bmm, Hm, rb);
 MPCB_UNROLL
         for (int i = 0; i < NXA * NXA; ++i) A[i] = 0.0;
 MPCB_UNROLL

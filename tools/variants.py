@@ -12,6 +12,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 VARIANTS = {
     "default": "",
+    "full_first_eval": "-DMPCB_EVAL_FIRST=0",
 }
 # KKT kernel occupancy (profiles/r02_variants_kktocc.txt): "-DMPCB_KKT_MINBLOCKS=1" (118 regs) | "=5" (96) | "=6" (80)
 # line search fused into the KKT warp: "-DMPCB_FUSE_LS=1" (profiles/r02_variants_fuse.txt)
