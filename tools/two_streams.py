@@ -10,6 +10,7 @@ from mpc_code_b200.mpc_loop import CompiledProblem
 
 G = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 K = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+STAGGER_MS = float(sys.argv[3]) if len(sys.argv) > 3 else 0.0      # group g starts g * STAGGER_MS late (phase offset)
 B = bench.BATCH_PER_GPU
 prob, ss, ocp = bench._problem()
 cp = CompiledProblem(prob, "nmpc_cstr")
@@ -26,6 +27,8 @@ for g in range(G):
 torch.cuda.synchronize()
 
 def run(g, k0, k1):
+    if STAGGER_MS > 0:
+        time.sleep(1e-3 * STAGGER_MS * g)
     with torch.cuda.stream(streams[g]):
         for k in range(k0, k1):
             ctls[g].step_fused(noises[g][k])
@@ -36,4 +39,4 @@ for phase, (k0, k1) in (("warmup", (0, 5)), ("timed", (5, 5 + K))):
     th = [threading.Thread(target=run, args=(g, k0, k1)) for g in range(G)]
     [t.start() for t in th]; [t.join() for t in th]
     torch.cuda.synchronize(); dt = time.time() - t0
-    print(phase, "groups", G, "steps/s %.0f  ms/step %.2f" % (B * (k1 - k0) / dt, 1e3 * dt / (k1 - k0)), flush=True)
+    print(phase, "groups", G, "stagger_ms", STAGGER_MS, "steps/s %.0f  ms/step %.2f" % (B * (k1 - k0) / dt, 1e3 * dt / (k1 - k0)), flush=True)
