@@ -126,6 +126,22 @@ class BatchedMpc:
             self.dhat_k = t.where(m, self.dhat0, self.dhat_k)
         self.P_k = t.where(m, self.P0, self.P_k)
 
+    def _row(self, v, slot=None):
+        """``[B, n]`` device tensor holding the host vector ``v`` in every row.  With ``slot`` the tensor is cached by value:
+        the host-side parameter vectors are constant in most problems, and an upload from pageable host memory synchronises
+        the stream, which would stop the host from enqueueing the next step ahead of the GPU."""
+        t = self.torch
+        a = np.ascontiguousarray(np.asarray(v, dtype=float).reshape(1, -1))
+        if slot is None:
+            return t.as_tensor(a, device=self.h.device).expand(self.B, -1).contiguous()
+        cache = self.__dict__.setdefault("_row_cache", {})
+        key = a.tobytes()
+        hit = cache.get(slot)
+        if hit is None or hit[0] != key:
+            hit = (key, t.as_tensor(a, device=self.h.device).expand(self.B, -1).contiguous())
+            cache[slot] = hit
+        return hit[1]
+
     def _params(self, t_k):
         """Time-varying parameters along the horizon (``MPC_code.py:492-515``)."""
         p, ns = self.prob, self.prob.ns
@@ -156,7 +172,7 @@ class BatchedMpc:
         t_k = self.ksim * p.h
         tt = t.full((B, 1), t_k, device=dev, dtype=f64)
         p_xk, p_yk, p_xmp, p_ymp, p_xp, p_yp = self._params(t_k)
-        row = lambda v: t.as_tensor(np.asarray(v, dtype=float).reshape(1, -1), device=dev).expand(B, -1).contiguous()  # noqa: E731
+        row = self._row
         p_x_k, p_y_k = row(p_xk[:, 0]), row(p_yk[:, 0])
         out: Dict[str, object] = dict(Xp=self.x_k.clone(), X_HAT=self.xhat_k.clone())
         nominal = p.flags["Fp_nominal"] is True
@@ -238,7 +254,7 @@ class BatchedMpc:
         if nominal:
             self.x_k = h.model_step(self.x_k, self.u_k, self.dhat_k, tt, row(p_xmp))
         else:
-            self.x_k = h.plant_step(self.x_k, self.u_k, tt, row(p_xp), row(p_xmp))
+            self.x_k = h.plant_step(self.x_k, self.u_k, tt, row(p_xp, "pxp"), row(p_xmp, "pxmp"))
         if state_noise is not None:
             self.x_k = self.x_k + h.tensor(state_noise, p.nxp)
         self._bury(t.isnan(self.x_k).any(dim=1))                                                           # :819-821
@@ -270,10 +286,10 @@ class BatchedMpc:
         self._tt.fill_(t_k)
         tt = self._tt
         p_xk, p_yk, p_xmp, p_ymp, p_xp, p_yp = self._params(t_k)
-        row = lambda v: t.as_tensor(np.asarray(v, dtype=float).reshape(1, -1), device=dev).expand(B, -1).contiguous()  # noqa: E731
+        row = self._row
         varying = any(k in p.ns for k in ("def_px", "def_py"))
-        px = row(p_xk.reshape(-1, order="F")) if varying else None
-        py = row(p_yk.reshape(-1, order="F")) if varying else None
+        px = row(p_xk.reshape(-1, order="F"), "px") if varying else None
+        py = row(p_yk.reshape(-1, order="F"), "py") if varying else None
         out: Dict[str, object] = {}
         if record_prediction:                               # x(k|k-1) as the reference logs it (MPC_code.py:520)
             out["X_HAT"] = h.loop_state()[0][:, :p.nx].contiguous()
@@ -281,7 +297,7 @@ class BatchedMpc:
             out["Xp"] = self.x_k.clone()
             if p.flags["Fp_nominal"] is True:
                 raise NotImplementedError("fused step with a nominal plant: pass y_meas")
-            y_meas = h.plant_meas(self.x_k, self.u_k, tt, row(p_yp), row(p_ymp), noise)
+            y_meas = h.plant_meas(self.x_k, self.u_k, tt, row(p_yp, "pyp"), row(p_ymp, "pymp"), noise)
             simulate = True
         else:
             simulate = False
@@ -290,14 +306,14 @@ class BatchedMpc:
         if getattr(self, "_sp_key", object()) != sp_key or getattr(self, "_sp", None) is None:
             vals = p.defSP(t_k) if p.defSP is not None else (np.zeros(p.ny), np.zeros(p.nu), np.zeros(p.nx))
             ysp, usp, xsp = [np.asarray(v, dtype=float).ravel() for v in vals]
-            self._sp = row(np.concatenate([usp, ysp, xsp])); self._sp_key = sp_key
+            self._sp = row(np.concatenate([usp, ysp, xsp]), "sp"); self._sp_key = sp_key     # uploaded only when the values change
         o = h.step(self.est_type, y_meas, tt, self._sp, px, py)
         self.u_k = o["u"]
         self.dead |= o["status"] == -13          # Invalid_Number_Detected: diverged instance, frozen (MPC_code.py:671-673 exits)
         out.update(U=o["u"], X_CORR=o["xhat"], D_HAT=o["dhat"], XS=o["xs"], US=o["us"], F_DYN=o["f"],
                    STATUS_DYN=o["status"], ITER_DYN=o["iters"], STATUS_SS=o["status_ss"])
         if simulate:
-            self.x_k = h.plant_step(self.x_k, self.u_k, tt, row(p_xp), row(p_xmp))
+            self.x_k = h.plant_step(self.x_k, self.u_k, tt, row(p_xp, "pxp"), row(p_xmp, "pxmp"))
         self.ksim += 1
         return out
 
