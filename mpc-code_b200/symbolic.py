@@ -144,6 +144,16 @@ _PYFUN = {
 }
 
 
+def _after(a: Expr, b: Expr) -> bool:
+    """Canonical operand order of the commutative operations: non-constants by creation order, constants last.
+    Constants are interned for the life of the process, so their uid says when some EARLIER trace first used the value;
+    ordering by it made the generated text (and with it the library digest) depend on what had been traced before."""
+    ac, bc = a.op == "const", b.op == "const"
+    if ac != bc:
+        return ac
+    return a.uid > b.uid
+
+
 def add(a: Expr, b: Expr) -> Expr:
     if a.op == "const" and b.op == "const":
         return const(a.val + b.val)
@@ -155,7 +165,7 @@ def add(a: Expr, b: Expr) -> Expr:
         return sub(a, b.args[0])
     if a.op == "neg":
         return sub(b, a.args[0])
-    if a.uid > b.uid:  # canonical order (commutative)
+    if _after(a, b):  # canonical order (commutative)
         a, b = b, a
     return _mk("add", a, b)
 
@@ -205,7 +215,7 @@ def mul(a: Expr, b: Expr) -> Expr:
         return neg(mul(a, b.args[0]))
     if a is b:
         return unary("sq", a)
-    if a.uid > b.uid:
+    if _after(a, b):
         a, b = b, a
     return _mk("mul", a, b)
 
