@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """Delete stale artefacts from mpc-code_b200/_build and oracle/_build: everything whose name does not carry the digest of
 a library / harness / oracle module that the CURRENT sources produce (`__graft_entry__.build()` is run first, so the
-current ones exist).  Keeps the gpurun snapshot small.   python tools/prune_build.py [--dry-run]"""
+current ones exist).  Keeps the gpurun snapshot small.  Also removes what only the tests build (`ref_*` libraries of the
+reference's example files, temporary examples, harnesses): the next `pytest -m "not gpu"` run rebuilds those, which takes
+minutes - so run the CPU suite once after pruning.   python tools/prune_build.py [--dry-run]"""
 import os
 import re
 import shutil
